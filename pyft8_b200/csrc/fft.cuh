@@ -1,0 +1,246 @@
+// fft.cuh -- shared-memory Stockham FFT building blocks (radix 2/3/4/5/8/16), fp32 complex.
+//
+// Every transform on the FT8 receive path has a length with factors 2, 3 and 5 only
+// (3840 = 2*1920 real, 192000 = 2*(375*256) real, 3200, 32), so the library
+// carries its own mixed-radix kernels instead of calling cuFFT: the transforms are fused with
+// windowing / untangling / log-magnitude (S1), band extraction + taper (F3) and the per-symbol
+// DFTs that follow them, which a library call cannot do.
+//
+// Formulation: decimation-in-frequency Stockham autosort.  A transform of length N runs as a
+// sequence of passes (R, S) with S = product of the radices already done; pass (R,S) maps
+//     y[q + S*(R*p + k)] = w_{N/S}^{p*k} * sum_j x[q + S*(p + M*j)] * w_R^{j*k},   M = N/(S*R)
+// for p < M, q < S.  Natural order in, natural order out, no bit reversal.  Twiddles come from a
+// table W[j] = exp(-2*pi*i*j/N) computed in double on the host (w_{N/S}^{p*k} = W[p*k*S]).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ft8 {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV> __device__ __forceinline__ float2 rot90(float2 a) {
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+template <int R, bool INV> struct Dft;
+
+template <bool INV> struct Dft<2, INV> {
+    static __device__ __forceinline__ void run(float2* a) {
+        float2 t = a[0];
+        a[0] = cadd(t, a[1]);
+        a[1] = csub(t, a[1]);
+    }
+};
+
+template <bool INV> struct Dft<3, INV> {
+    static __device__ __forceinline__ void run(float2* a) {
+        const float s = 0.86602540378443864676f;
+        float2 t = cadd(a[1], a[2]);
+        float2 d = rot90<INV>(csub(a[1], a[2]));       // -/+ i*(a1-a2)
+        float2 m = make_float2(fmaf(-0.5f, t.x, a[0].x), fmaf(-0.5f, t.y, a[0].y));
+        a[0] = cadd(a[0], t);
+        a[1] = make_float2(fmaf(s, d.x, m.x), fmaf(s, d.y, m.y));
+        a[2] = make_float2(fmaf(-s, d.x, m.x), fmaf(-s, d.y, m.y));
+    }
+};
+
+template <bool INV> struct Dft<4, INV> {
+    static __device__ __forceinline__ void run(float2* a) {
+        float2 s02 = cadd(a[0], a[2]), d02 = csub(a[0], a[2]);
+        float2 s13 = cadd(a[1], a[3]), d13 = rot90<INV>(csub(a[1], a[3]));
+        a[0] = cadd(s02, s13);
+        a[2] = csub(s02, s13);
+        a[1] = cadd(d02, d13);
+        a[3] = csub(d02, d13);
+    }
+};
+
+template <bool INV> struct Dft<5, INV> {
+    static __device__ __forceinline__ void run(float2* a) {
+        const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+        const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+        float2 t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]);
+        float2 t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
+        float2 m1 = make_float2(fmaf(c1, t1.x, fmaf(c2, t2.x, a[0].x)), fmaf(c1, t1.y, fmaf(c2, t2.y, a[0].y)));
+        float2 m2 = make_float2(fmaf(c2, t1.x, fmaf(c1, t2.x, a[0].x)), fmaf(c2, t1.y, fmaf(c1, t2.y, a[0].y)));
+        float2 n1 = rot90<INV>(make_float2(fmaf(s1, t3.x, s2 * t4.x), fmaf(s1, t3.y, s2 * t4.y)));
+        float2 n2 = rot90<INV>(make_float2(fmaf(s2, t3.x, -s1 * t4.x), fmaf(s2, t3.y, -s1 * t4.y)));
+        a[0] = cadd(a[0], cadd(t1, t2));
+        a[1] = cadd(m1, n1);
+        a[4] = csub(m1, n1);
+        a[2] = cadd(m2, n2);
+        a[3] = csub(m2, n2);
+    }
+};
+
+// 8 = 2 x 4 in registers: j = 4*j1 + j2, k = k1 + 2*k2
+template <bool INV> struct Dft<8, INV> {
+    static __device__ __forceinline__ void run(float2* a) {
+        const float h = 0.70710678118654752440f;
+        float2 c[2][4];
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+            c[0][j2] = cadd(a[j2], a[4 + j2]);
+            c[1][j2] = csub(a[j2], a[4 + j2]);
+        }
+        // twiddle w8^(j2*k1) on the k1 = 1 row
+        {
+            float2 v = c[1][1];   // * w8^1 = (1 -/+ i)/sqrt2
+            c[1][1] = INV ? make_float2(h * (v.x - v.y), h * (v.x + v.y)) : make_float2(h * (v.x + v.y), h * (v.y - v.x));
+            c[1][2] = rot90<INV>(c[1][2]);
+            v = c[1][3];          // * w8^3 = (-1 -/+ i)/sqrt2
+            c[1][3] = INV ? make_float2(-h * (v.x + v.y), h * (v.x - v.y)) : make_float2(h * (v.y - v.x), -h * (v.x + v.y));
+        }
+        Dft<4, INV>::run(c[0]);
+        Dft<4, INV>::run(c[1]);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+            a[2 * k2] = c[0][k2];
+            a[2 * k2 + 1] = c[1][k2];
+        }
+    }
+};
+
+// 16 = 4 x 4 in registers: j = 4*j1 + j2, k = k1 + 4*k2
+template <bool INV> struct Dft<16, INV> {
+    static __device__ __forceinline__ void run(float2* a) {
+        const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+        float2 c[4][4];   // c[k1][j2]
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+            float2 t[4] = {a[j2], a[4 + j2], a[8 + j2], a[12 + j2]};
+            Dft<4, INV>::run(t);
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1) c[k1][j2] = t[k1];
+        }
+        // twiddles w16^(j2*k1), k1,j2 in 1..3 : exponents 1,2,3 / 2,4,6 / 3,6,9
+        const float2 w1 = make_float2(c1, -s1), w2 = make_float2(h, -h), w3 = make_float2(s1, -c1);
+        const float2 w6 = make_float2(-h, -h), w9 = make_float2(-c1, s1);
+#define FT8_TW(v, w) v = INV ? cmulc(v, w) : cmul(v, w)
+        FT8_TW(c[1][1], w1); FT8_TW(c[1][2], w2); FT8_TW(c[1][3], w3);
+        FT8_TW(c[2][1], w2); c[2][2] = rot90<INV>(c[2][2]); FT8_TW(c[2][3], w6);
+        FT8_TW(c[3][1], w3); FT8_TW(c[3][2], w6); FT8_TW(c[3][3], w9);
+#undef FT8_TW
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+            Dft<4, INV>::run(c[k1]);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) a[k1 + 4 * k2] = c[k1][k2];
+        }
+    }
+};
+
+// One Stockham pass for butterfly t (0 <= t < N/R).  x, y may be any addressable memory.
+// W is the length-N twiddle table (W[j] = exp(-2 pi i j / N)), read through the read-only path.
+template <int N, int R, int S> struct Pass {
+    static constexpr int M = N / (S * R);
+    static __device__ __forceinline__ void load(const float2* x, int t, float2* a) {
+        const int p = t / S, q = t - p * S;
+#pragma unroll
+        for (int j = 0; j < R; ++j) a[j] = x[q + S * (p + M * j)];
+    }
+    template <bool INV>
+    static __device__ __forceinline__ void compute_store(float2* y, int t, float2* a, const float2* __restrict__ W) {
+        const int p = t / S, q = t - p * S;
+        Dft<R, INV>::run(a);
+        y[q + S * (R * p)] = a[0];
+#pragma unroll
+        for (int k = 1; k < R; ++k) {
+            float2 v = a[k];
+            if (M > 1) {
+                float2 w = __ldg(&W[p * k * S]);
+                v = INV ? cmulc(v, w) : cmul(v, w);
+            }
+            y[q + S * (R * p + k)] = v;
+        }
+    }
+};
+
+// In-place pass over a shared-memory buffer by a group of NT threads (lt = thread index in the group):
+// all operands are read into registers, the group synchronises (sync functor), then results are written.
+template <int N, int R, int S, int NT, bool INV, class Sync>
+__device__ __forceinline__ void pass_inplace(float2* buf, int lt, const float2* __restrict__ W, Sync sync) {
+    constexpr int NBF = N / R;
+    constexpr int PER = (NBF + NT - 1) / NT;
+    float2 a[PER][R];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int t = lt + i * NT;
+        if (t < NBF) Pass<N, R, S>::load(buf, t, a[i]);
+    }
+    sync();
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int t = lt + i * NT;
+        if (t < NBF) Pass<N, R, S>::template compute_store<INV>(buf, t, a[i], W);
+    }
+    sync();
+}
+
+struct CtaSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// Complete in-place transforms for the sizes on the path (NT threads cooperate, CTA-wide barriers).
+template <int NT, bool INV> __device__ __forceinline__ void fft1920(float2* buf, int lt, const float2* __restrict__ W) {
+    pass_inplace<1920, 3, 1, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<1920, 5, 3, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<1920, 8, 15, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<1920, 16, 120, NT, INV>(buf, lt, W, CtaSync());
+}
+template <int NT, bool INV> __device__ __forceinline__ void fft3200(float2* buf, int lt, const float2* __restrict__ W) {
+    pass_inplace<3200, 5, 1, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<3200, 5, 5, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<3200, 8, 25, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<3200, 16, 200, NT, INV>(buf, lt, W, CtaSync());
+}
+template <int NT, bool INV> __device__ __forceinline__ void fft375(float2* buf, int lt, const float2* __restrict__ W) {
+    pass_inplace<375, 3, 1, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<375, 5, 3, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<375, 5, 15, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<375, 5, 75, NT, INV>(buf, lt, W, CtaSync());
+}
+template <int NT, bool INV> __device__ __forceinline__ void fft256(float2* buf, int lt, const float2* __restrict__ W) {
+    pass_inplace<256, 16, 1, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<256, 16, 16, NT, INV>(buf, lt, W, CtaSync());
+}
+template <int NT, bool INV> __device__ __forceinline__ void fft32(float2* buf, int lt, const float2* __restrict__ W) {
+    pass_inplace<32, 8, 1, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<32, 4, 8, NT, INV>(buf, lt, W, CtaSync());
+}
+
+// Batched variant: NB independent transforms of length N stored back to back in `buf`.
+template <int N, int R, int S, int NB, int NT, bool INV>
+__device__ __forceinline__ void pass_inplace_batched(float2* buf, int tid, const float2* __restrict__ W) {
+    constexpr int NBF = N / R;
+    constexpr int ITEMS = NBF * NB;
+    constexpr int PER = (ITEMS + NT - 1) / NT;
+    float2 a[PER][R];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int it = tid + i * NT;
+        if (it < ITEMS) {
+            const int b = it / NBF, t = it - b * NBF;
+            Pass<N, R, S>::load(buf + b * N, t, a[i]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int it = tid + i * NT;
+        if (it < ITEMS) {
+            const int b = it / NBF, t = it - b * NBF;
+            Pass<N, R, S>::template compute_store<INV>(buf + b * N, t, a[i], W);
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace ft8

@@ -1,0 +1,277 @@
+// fine.cuh -- F1 (cycle spectrum) and F2/F3 (per-candidate fine time/frequency sync).
+//
+// F1 restates AudioIn.get_cycle_spectrum (receiver.py:280-286): rfft of the 180000-sample cycle
+// zero-padded to 192000 (0.0625 Hz bins).  The real transform is a 96000-point complex transform
+// of z[n] = x[2n] + i x[2n+1], done four-step as 375 x 256:
+//   A (k_cs_cols): for 16 columns n2 at a time, 375-point FFTs over n1 (n = 256 n1 + n2) in shared
+//                  memory, times w_96000^(n2 k1), to scratch Y[k1][n2];
+//   B (k_cs_rows): 256-point FFTs of rows k1 and of their mirror rows 375-k1, then the real-FFT
+//                  untangle for bins k = k1 + 375 k2 and 96000-k in the same CTA.
+// Only bins [1418, 48832) are ever read by the fine stage; the pipeline keeps bins
+// < FINE_SPEC_STRIDE, the stand-alone op writes all 96001.
+//
+// F2/F3 restate Candidate._get_llr_fine / _get_signal_grid_fine (receiver.py:140-206):
+// one CTA per candidate; 1000 bins around fb -> taper (upper edge taper is inverted in the reference and
+// is reproduced as is) -> 3200-point inverse FFT in shared memory (first pass gathers the band straight
+// from global memory; 2200 of its 3200 inputs are structurally zero) -> 32-sample symbol DFTs.
+// 8 time tweaks share one inverse FFT; 9 frequency tweaks need one each; the best one is kept in a second
+// shared buffer so the final 79x8 grid needs no recomputation.  Only the MIDDLE Costas block is scored.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fft.cuh"
+#include "sync.cuh"
+
+namespace ft8 {
+
+constexpr int CS_N = 96000, CS_N1 = 375, CS_N2 = 256, CS_COLS = 16, CS_NT = 256;
+constexpr int FINE_SPEC_STRIDE = 49152;
+constexpr int FINE_N = 3200, FINE_NT = 256;
+
+template <typename T> __device__ __forceinline__ float2 load_pair(const T* x, int n);
+template <> __device__ __forceinline__ float2 load_pair<int16_t>(const int16_t* x, int n) {
+    const short2 v = *reinterpret_cast<const short2*>(x + 2 * n);
+    return make_float2((float)v.x, (float)v.y);
+}
+template <> __device__ __forceinline__ float2 load_pair<float>(const float* x, int n) {
+    return *reinterpret_cast<const float2*>(x + 2 * n);
+}
+
+// grid (16, B).  Y: [B][375][256] float2.
+template <typename T>
+__global__ void __launch_bounds__(CS_NT)
+k_cs_cols(const T* __restrict__ audio, float2* __restrict__ Y, const float2* __restrict__ W375,
+          const float2* __restrict__ W96000) {
+    extern __shared__ float2 cs_smem[];          // [16][375]
+    const int cyc = blockIdx.y, n2_0 = blockIdx.x * CS_COLS;
+    const T* x = audio + (size_t)cyc * CYCLE_SAMPLES;
+    for (int i = threadIdx.x; i < CS_COLS * CS_N1; i += CS_NT) {
+        const int n1 = i / CS_COLS, c = i - n1 * CS_COLS;
+        const int n = CS_N2 * n1 + n2_0 + c;
+        cs_smem[c * CS_N1 + n1] = (n < CYCLE_SAMPLES / 2) ? load_pair<T>(x, n) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    pass_inplace_batched<375, 3, 1, CS_COLS, CS_NT, false>(cs_smem, threadIdx.x, W375);
+    pass_inplace_batched<375, 5, 3, CS_COLS, CS_NT, false>(cs_smem, threadIdx.x, W375);
+    pass_inplace_batched<375, 5, 15, CS_COLS, CS_NT, false>(cs_smem, threadIdx.x, W375);
+    pass_inplace_batched<375, 5, 75, CS_COLS, CS_NT, false>(cs_smem, threadIdx.x, W375);
+    float2* y = Y + (size_t)cyc * CS_N;
+    for (int i = threadIdx.x; i < CS_COLS * CS_N1; i += CS_NT) {
+        const int k1 = i / CS_COLS, c = i - k1 * CS_COLS;
+        const int n2 = n2_0 + c;
+        const float2 w = __ldg(&W96000[n2 * k1]);
+        y[k1 * CS_N2 + n2] = cmul(cs_smem[c * CS_N1 + k1], w);
+    }
+}
+
+constexpr int CSR_G = 8;      // k1 values per CTA (plus their mirrors)
+// grid (24, B): k1 in {0} u [1,187] in groups of 8.  spec: [B][spec_stride] float2, bins <= kmax written.
+__global__ void __launch_bounds__(CS_NT)
+k_cs_rows(const float2* __restrict__ Y, float2* __restrict__ spec, int spec_stride, int kmax,
+          const float2* __restrict__ W256, const float2* __restrict__ W192000) {
+    __shared__ float2 rows[2 * CSR_G][CS_N2];     // [0..7] rows k1, [8..15] mirror rows 375-k1
+    const int cyc = blockIdx.y, g0 = blockIdx.x * CSR_G;
+    const float2* y = Y + (size_t)cyc * CS_N;
+    for (int i = threadIdx.x; i < 2 * CSR_G * CS_N2; i += CS_NT) {
+        const int r = i / CS_N2, c = i - r * CS_N2;
+        const int k1 = g0 + (r & (CSR_G - 1));
+        float2 v = make_float2(0.f, 0.f);
+        if (k1 <= 187) {
+            const int row = (r < CSR_G) ? k1 : (CS_N1 - k1) % CS_N1;
+            v = y[row * CS_N2 + c];
+        }
+        rows[r][c] = v;
+    }
+    __syncthreads();
+    pass_inplace_batched<256, 16, 1, 2 * CSR_G, CS_NT, false>(&rows[0][0], threadIdx.x, W256);
+    pass_inplace_batched<256, 16, 16, 2 * CSR_G, CS_NT, false>(&rows[0][0], threadIdx.x, W256);
+    float2* out = spec + (size_t)cyc * spec_stride;
+    for (int i = threadIdx.x; i < CSR_G * CS_N2; i += CS_NT) {
+        const int k2 = i / CSR_G, r = i - k2 * CSR_G;
+        const int k1 = g0 + r;
+        if (k1 > 187) continue;
+        const int k = k1 + CS_N1 * k2;                      // bin of the complex transform
+        // partner Z[96000-k] sits in the mirror row at column 255-k2 (k1 > 0) or (256-k2)%256 (k1 == 0)
+        const int k2m = (k1 == 0) ? ((CS_N2 - k2) & (CS_N2 - 1)) : (CS_N2 - 1 - k2);
+        const float2 zk = rows[r][k2];
+        const float2 zm = rows[CSR_G + r][k2m];
+        const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        const float2 wo = cmul(o, __ldg(&W192000[k]));
+        if (k <= kmax) out[k] = cadd(e, wo);
+        const int km = CS_N - k;                            // mirrored output bin, conj(E - W O)
+        if (km <= kmax && !(k1 == 0 && k2 > 128)) out[km] = make_float2(e.x - wo.x, -(e.y - wo.y));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- F2/F3
+struct FineTables {
+    float taper[100];          // 0.5*(1+cos(linspace(-pi,0,100))): rises 0 -> 1
+    float2 w32[32];            // exp(-2 pi i m / 32)
+};
+__constant__ FineTables c_fine;
+
+struct FineOut {               // per candidate
+    int32_t tt, ff, nsync;
+    float sd;
+    int32_t snr;
+};
+
+// first inverse pass (R=5, S=1, M=640) with operands gathered from the cycle spectrum:
+// a[i] = spec[fb + i] for i < 850 (taper on [750,850)), spec[fb + i - 3200] for i >= 3050 (taper on [3050,3150)), else 0
+__device__ __forceinline__ float2 fine_band_at(const float2* __restrict__ spec, int fb, int i) {
+    if (i < 850) {
+        float2 v = __ldg(&spec[fb + i]);
+        if (i >= 750) { const float t = c_fine.taper[i - 750]; v.x *= t; v.y *= t; }
+        return v;
+    }
+    if (i >= 3050) {
+        float2 v = __ldg(&spec[fb + i - 3200]);
+        if (i < 3150) { const float t = c_fine.taper[i - 3050]; v.x *= t; v.y *= t; }
+        return v;
+    }
+    return make_float2(0.f, 0.f);
+}
+
+__device__ __forceinline__ void fine_ifft(float2* buf, const float2* __restrict__ spec, int fb, int tid,
+                                          const float2* __restrict__ W3200) {
+    constexpr int NBF = 640, PER = (NBF + FINE_NT - 1) / FINE_NT;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int p = tid + i * FINE_NT;
+        if (p < NBF) {
+            float2 a[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) a[j] = fine_band_at(spec, fb, p + 640 * j);
+            Pass<3200, 5, 1>::template compute_store<true>(buf, p, a, W3200);
+        }
+    }
+    __syncthreads();
+    pass_inplace<3200, 5, 5, FINE_NT, true>(buf, tid, W3200, CtaSync());
+    pass_inplace<3200, 8, 25, FINE_NT, true>(buf, tid, W3200, CtaSync());
+    pass_inplace<3200, 16, 200, FINE_NT, true>(buf, tid, W3200, CtaSync());
+}
+
+// |DFT32(z[i0 : i0+32])[t]| / 3200  (numpy's ifft carries the 1/N)
+__device__ __forceinline__ float tone_mag(const float2* z, int i0, int t) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 8
+    for (int m = 0; m < 32; ++m) {
+        const float2 w = c_fine.w32[(t * m) & 31];
+        const float2 v = z[i0 + m];
+        acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
+        acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
+    }
+    return sqrtf(fmaf(acc.x, acc.x, acc.y * acc.y)) * (1.0f / 3200.0f);
+}
+
+__device__ __forceinline__ int clip_start(int i) { return max(0, min(FINE_N - 32, i)); }
+
+// middle-Costas score for a window start tb (receiver.py:203): g49[49] scratch, result broadcast through *res
+__device__ __forceinline__ float costas_score(const float2* z, int tb, float* g49, int tid) {
+    if (tid < 49) {
+        const int k = tid / 7, t = tid - 7 * k;
+        g49[tid] = tone_mag(z, clip_start(tb + 32 * (36 + k)), t);
+    }
+    __syncthreads();
+    float s = 0.f;
+    for (int i = 0; i < 49; ++i) {
+        const int k = i / 7, t = i - 7 * k;
+        s = fmaf(g49[i], (t == c_costas[k]) ? 1.0f : (-1.0f / 6.0f), s);
+    }
+    __syncthreads();
+    return s;      // every thread computes the same value
+}
+
+constexpr int FINE_SMEM_BYTES = 2 * FINE_N * (int)sizeof(float2) + 79 * 8 * (int)sizeof(float) + 8 * 49 * (int)sizeof(float);
+
+// One CTA per work item (grid-stride over list[0..*count)).  cand arrays are indexed by the global slot id.
+// spec: [B][spec_stride] float2.  Outputs per slot: fo[slot], llr_fine[slot][174], optional sig_grid[slot][79][8].
+__global__ void __launch_bounds__(FINE_NT)
+k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restrict__ list, const int32_t* __restrict__ count,
+       int n_direct, const int32_t* __restrict__ cycle_of, const int16_t* __restrict__ cand_f0,
+       const int16_t* __restrict__ cand_h0, const float2* __restrict__ W3200, FineOut* __restrict__ fo,
+       float* __restrict__ llr_fine, float* __restrict__ sig_grid) {
+    extern __shared__ float2 fine_smem[];
+    float2* zb[2] = {fine_smem, fine_smem + FINE_N};
+    float* G = reinterpret_cast<float*>(fine_smem + 2 * FINE_N);      // [79][8]
+    float* g49 = G + 79 * 8;                                          // [8][49]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n_items = list ? *count : n_direct;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int slot = list ? list[item] : item;
+        const int cyc = cycle_of[slot];
+        const int f0 = cand_f0[slot], h0 = cand_h0[slot];
+        const float2* sp = spec + (size_t)cyc * spec_stride;
+        const int fb0 = 50 * f0;                                   // int(0.5 + 16*fHz), fHz = 3.125*f0
+        const int tb0 = (h0 >= 0) ? 8 * h0 : 8 * h0 + 1;           // int(0.5 + 200*tsec) truncates toward zero
+        // ---- time scan at ftweak = 0
+        fine_ifft(zb[0], sp, fb0, tid, W3200);
+        for (int i = tid; i < 8 * 49; i += FINE_NT) {
+            const int ti = i / 49, r = i - 49 * ti;
+            const int k = r / 7, t = r - 7 * k;
+            g49[i] = tone_mag(zb[0], clip_start(tb0 + (-8 + 2 * ti) + 32 * (36 + k)), t);
+        }
+        __syncthreads();
+        int tt = -8;
+        {
+            float best = 0.f;
+            for (int ti = 0; ti < 8; ++ti) {
+                float s = 0.f;
+                for (int i = 0; i < 49; ++i) {
+                    const int k = i / 7, t = i - 7 * k;
+                    s = fmaf(g49[ti * 49 + i], (t == c_costas[k]) ? 1.0f : (-1.0f / 6.0f), s);
+                }
+                if (ti == 0 || s > best) { best = s; tt = -8 + 2 * ti; }
+            }
+        }
+        __syncthreads();
+        // ---- frequency scan at the chosen time tweak; keep the best baseband in zb[keep]
+        int keep = 0, ff = -32;
+        float bestf = 0.f;
+        for (int fi = 0; fi < 9; ++fi) {
+            const int cur = (fi == 0) ? 0 : (keep ^ 1);
+            fine_ifft(zb[cur], sp, fb0 + (-32 + 8 * fi), tid, W3200);
+            const float s = costas_score(zb[cur], tb0 + tt, g49, tid);
+            if (fi == 0 || s > bestf) { bestf = s; ff = -32 + 8 * fi; keep = cur; }
+        }
+        // ---- final grid from the kept baseband
+        const float2* z = zb[keep];
+        for (int i = tid; i < 79 * 8; i += FINE_NT) {
+            const int j = i >> 3, t = i & 7;
+            G[i] = tone_mag(z, clip_start(tb0 + tt + 32 * j), t);
+        }
+        __syncthreads();
+        if (sig_grid) for (int i = tid; i < 79 * 8; i += FINE_NT) sig_grid[(size_t)slot * 632 + i] = G[i];
+        if (tid < 32) {
+            int hit = 0;
+            if (lane < 21) {
+                const int blk = lane / 7, k = lane - 7 * blk;
+                const int row = (blk == 0) ? k : (blk == 1 ? 36 + k : 72 + k);
+                int am = 0;
+                float mv = G[row * 8];
+                for (int t = 1; t < 8; ++t) if (G[row * 8 + t] > mv) { mv = G[row * 8 + t]; am = t; }
+                hit = (am == c_costas[k]) ? 1 : 0;
+            }
+            const int nsync = __reduce_add_sync(0xffffffffu, hit);
+            float p[2][8];
+            if (lane < 29) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int sym = c_payload_sym[lane + 29 * q];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) p[q][t] = 20.0f * log10f(G[sym * 8 + t]);
+                }
+            }
+            float sd; int snr;
+            llr_from_payload_warp(p, lane, llr_fine + (size_t)slot * 174, sd, snr);
+            if (lane == 0) {
+                FineOut o; o.tt = tt; o.ff = ff; o.nsync = nsync; o.sd = sd; o.snr = snr;
+                fo[slot] = o;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace ft8

@@ -1,0 +1,791 @@
+// ft8_b200.cu -- handle, table upload and the C ABI (include/ft8_b200.h) of the B200-native FT8 receive path.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see __graft_entry__.build).
+// One handle = one device + one stream + constant tables + scratch sized from ft8_cfg.max_cycles.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/ft8_b200.h"
+#include "ft8_tables.h"
+#include "fft.cuh"
+#include "codec.cuh"
+#include "ldpc.cuh"
+#include "osd.cuh"
+#include "spectrogram.cuh"
+#include "sync.cuh"
+#include "fine.cuh"
+#include "passes.cuh"
+#include "synth.cuh"
+
+using namespace ft8;
+
+static thread_local std::string g_create_error;
+
+struct ft8_handle {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    ft8_cfg cfg{};
+    std::string err;
+    // constant-like tables in global memory
+    float* d_hann = nullptr;
+    float2 *d_W1920 = nullptr, *d_W3840 = nullptr, *d_W3200 = nullptr, *d_W375 = nullptr, *d_W256 = nullptr,
+           *d_W96000 = nullptr, *d_W192000 = nullptr, *d_W32 = nullptr;
+    float* d_pulse = nullptr;        // GFSK pulse for the synthetic generator
+    // batch scratch
+    size_t cap_cycles = 0, cap_slots = 0;
+    void* d_audio = nullptr; size_t audio_bytes = 0;
+    float* d_grid = nullptr;
+    float2* d_Y = nullptr; size_t y_cycles = 0;
+    float2* d_spec = nullptr;
+    float* d_best_score = nullptr; int16_t* d_best_h0 = nullptr;
+    int16_t *d_f0 = nullptr, *d_h0 = nullptr; float* d_score = nullptr; int32_t* d_ncand = nullptr;
+    int32_t* d_cycle_of = nullptr;
+    uint8_t* d_status = nullptr; float* d_llr_grid = nullptr; float* d_grid_sd = nullptr; int8_t* d_grid_snr = nullptr;
+    float* d_llr_fine = nullptr; FineOut* d_fine = nullptr; float* d_saved = nullptr; uint8_t* d_saved_n = nullptr;
+    uint8_t* d_saved_ap = nullptr; uint32_t* d_bits = nullptr; uint8_t *d_ripass = nullptr, *d_rap = nullptr, *d_rmethod = nullptr;
+    uint16_t* d_rnits = nullptr; int32_t* d_osd_found = nullptr; uint32_t* d_osd_bits = nullptr;
+    int32_t *d_list_fine = nullptr, *d_list_osd = nullptr, *d_counts = nullptr;   // counts: [0] fine, [1] osd, [2] records
+    DevStats* d_stats = nullptr;
+    ft8_record* d_rec = nullptr;
+    ft8_record* h_rec = nullptr;      // pinned staging
+    int32_t* h_counts = nullptr;      // pinned
+    DevStats* h_stats = nullptr;      // pinned
+    // generic arena for the stand-alone stage ops
+    void* arena = nullptr; size_t arena_bytes = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float last_ms[3] = {0, 0, 0};
+    ft8_stats stats{};
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+            return FT8_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+static int fail(ft8_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------ tables
+static std::vector<float2> twiddles(int n, int count) {
+    std::vector<float2> w(count);
+    for (int j = 0; j < count; ++j) {
+        const double a = -2.0 * M_PI * (double)j / (double)n;
+        w[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    return w;
+}
+
+template <typename T> static cudaError_t upload(T** dst, const std::vector<T>& v) {
+    cudaError_t e = cudaMalloc((void**)dst, v.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static uint32_t crc14_bits(const uint8_t* msg77) {      // decoders.py:123-129
+    uint32_t r = 0;
+    for (int i = 0; i < 96; ++i) {
+        const uint32_t bit = (i < 77) ? msg77[i] : 0u;
+        const uint32_t top = (r >> 13) & 1u;
+        r = ((r << 1) & 0x3FFFu) | bit;
+        if (top) r ^= 0x2757u;
+    }
+    return r;
+}
+
+static cudaError_t upload_constant_tables() {
+    // CRC syndrome contributions
+    CodecTables ct;
+    memset(&ct, 0, sizeof(ct));
+    for (int j = 0; j < 91; ++j) {
+        if (j < 77) {
+            uint8_t m[77] = {0};
+            m[j] = 1;
+            ct.crc_syn[j] = (uint16_t)crc14_bits(m);
+        } else {
+            ct.crc_syn[j] = (uint16_t)(1u << (90 - j));
+        }
+    }
+    memcpy(ct.prefix2, FT8_PREFIX2_BITS, sizeof(ct.prefix2));
+    cudaError_t e = cudaMemcpyToSymbol(c_codec, &ct, sizeof(ct));
+    if (e != cudaSuccess) return e;
+    // LDPC graph; variable -> edge slots in np.add.at order (degree-6 group flattened first, then degree-7)
+    LdpcTables lt;
+    memset(&lt, 0, sizeof(lt));
+    int cnt[174] = {0};
+    for (int c = 0; c < 83; ++c)
+        for (int k = 0; k < 7; ++k) {
+            const uint8_t v = FT8_CHECK_VARS[c][k];
+            lt.chk_var[c * 7 + k] = v;
+            if (v != 255) lt.var_edge[3 * v + cnt[v]++] = (uint16_t)(c * 7 + k);
+        }
+    e = cudaMemcpyToSymbol(c_ldpc, &lt, sizeof(lt));
+    if (e != cudaSuccess) return e;
+    // OSD columns of G0 = [I | A^T]
+    OsdTables ot;
+    memset(&ot, 0, sizeof(ot));
+    for (int c = 0; c < 91; ++c) ot.col[c][c >> 5] = 1u << (c & 31);
+    for (int i = 0; i < 83; ++i)
+        for (int w = 0; w < 3; ++w) ot.col[91 + i][w] = FT8_GEN_MASK[i][w];
+    e = cudaMemcpyToSymbol(c_osd, &ot, sizeof(ot));
+    if (e != cudaSuccess) return e;
+    // AP patterns (receiver.py:21-27)
+    ApTables ap;
+    memset(&ap, 0, sizeof(ap));
+    const char* pat[5] = {"", "00000000000000000000000000100", "0111111001110101001", "0111111010010100001", "0111111010010010001"};
+    const int first[5] = {0, 0, 58, 58, 58};
+    for (int a = 0; a < 5; ++a) {
+        ap.first[a] = (int8_t)first[a];
+        ap.len[a] = (int8_t)strlen(pat[a]);
+        for (int i = 0; i < ap.len[a]; ++i) ap.bits[a][i] = pat[a][i] == '1';
+    }
+    e = cudaMemcpyToSymbol(c_ap, &ap, sizeof(ap));
+    if (e != cudaSuccess) return e;
+    // fine-stage tables
+    FineTables ft;
+    for (int i = 0; i < 100; ++i) {
+        const double x = -M_PI + M_PI * (double)i / 99.0;       // np.linspace(-pi, 0, 100); cos is even so the
+        ft.taper[i] = (float)(0.5 * (1.0 + cos(x)));             // (pi, 0) variant of receiver.py:183 is identical
+    }
+    for (int m = 0; m < 32; ++m) {
+        const double a = -2.0 * M_PI * m / 32.0;
+        ft.w32[m] = make_float2((float)cos(a), (float)sin(a));
+    }
+    return cudaMemcpyToSymbol(c_fine, &ft, sizeof(ft));
+}
+
+template <typename T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+static int ensure_arena(ft8_handle* h, size_t bytes) {
+    if (bytes <= h->arena_bytes) return FT8_OK;
+    if (h->arena) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->arena)); h->arena = nullptr; h->arena_bytes = 0; }
+    CK(cudaMalloc(&h->arena, bytes));
+    h->arena_bytes = bytes;
+    return FT8_OK;
+}
+
+static int ensure_audio(ft8_handle* h, size_t bytes) {
+    if (bytes <= h->audio_bytes) return FT8_OK;
+    if (h->d_audio) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->d_audio)); h->d_audio = nullptr; h->audio_bytes = 0; }
+    CK(cudaMalloc(&h->d_audio, bytes));
+    h->audio_bytes = bytes;
+    return FT8_OK;
+}
+
+extern "C" void ft8_default_cfg(ft8_cfg* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->max_cycles = 1;
+    cfg->max_cands = 200;
+    cfg->sync_score_min = 85.0f;
+    cfg->llr_sd_min = 5.0f;
+    cfg->osd_singleflips = 30;
+    cfg->osd_doubleflips = 2;
+    cfg->max_codewords = 1 << 16;
+}
+
+extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
+    if (!out) return fail(nullptr, FT8_E_BADARG, "ft8_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, FT8_E_NODEVICE, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, FT8_E_BADARG, "ft8_create: bad device index");
+    ft8_cfg cfg;
+    ft8_default_cfg(&cfg);
+    if (cfg_in) cfg = *cfg_in;
+    if (cfg.max_cycles <= 0) cfg.max_cycles = 1;
+    if (cfg.max_cands <= 0) cfg.max_cands = 200;
+    if (cfg.max_cands > N_F0) cfg.max_cands = N_F0;
+    if (cfg.osd_singleflips < 0 || cfg.osd_singleflips > OSD_MAX_FLIPS || cfg.osd_doubleflips < 0)
+        return fail(nullptr, FT8_E_BADARG, "ft8_create: osd flips out of range");
+    if (cfg.max_codewords <= 0) cfg.max_codewords = 1 << 16;
+    ft8_handle* h = new ft8_handle();
+    h->device = device;
+    h->cfg = cfg;
+#define CKC(call)                                                                              \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            g_create_error = std::string(#call) + ": " + cudaGetErrorString(e__);              \
+            ft8_destroy(h);                                                                    \
+            return FT8_E_CUDA;                                                                 \
+        }                                                                                      \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    h->n_sm = prop.multiProcessorCount;
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& ev : h->ev) CKC(cudaEventCreate(&ev));
+    CKC(upload_constant_tables());
+    {
+        std::vector<float> w(NFFT_S);
+        for (int i = 0; i < NFFT_S; ++i) {          // np.hanning: 0.5 + 0.5*cos(pi*n/(M-1)), n = 1-M, 3-M, ...
+            const double n = (double)(1 - NFFT_S + 2 * i);
+            w[i] = (float)(0.5 + 0.5 * cos(M_PI * n / (double)(NFFT_S - 1)));
+        }
+        CKC(upload(&h->d_hann, w));
+        CKC(upload(&h->d_W1920, twiddles(1920, 1920)));
+        CKC(upload(&h->d_W3840, twiddles(3840, 1921)));
+        CKC(upload(&h->d_W3200, twiddles(3200, 3200)));
+        CKC(upload(&h->d_W375, twiddles(375, 375)));
+        CKC(upload(&h->d_W256, twiddles(256, 256)));
+        CKC(upload(&h->d_W96000, twiddles(96000, 96000)));
+        CKC(upload(&h->d_W192000, twiddles(192000, 96001)));
+        CKC(upload(&h->d_W32, twiddles(32, 32)));
+        CKC(upload(&h->d_pulse, synth_pulse_table()));
+    }
+    const size_t B = (size_t)cfg.max_cycles, K = (size_t)cfg.max_cands, N = B * K;
+    h->cap_cycles = B;
+    h->cap_slots = N;
+    CKC(dmalloc(&h->d_grid, B * GRID_ROWS * GRID_COLS));
+    h->y_cycles = std::min<size_t>(B, 256);
+    CKC(dmalloc(&h->d_Y, h->y_cycles * CS_N));
+    CKC(dmalloc(&h->d_spec, B * FINE_SPEC_STRIDE));
+    CKC(dmalloc(&h->d_best_score, B * N_F0));
+    CKC(dmalloc(&h->d_best_h0, B * N_F0));
+    CKC(dmalloc(&h->d_f0, N)); CKC(dmalloc(&h->d_h0, N)); CKC(dmalloc(&h->d_score, N)); CKC(dmalloc(&h->d_ncand, B));
+    CKC(dmalloc(&h->d_cycle_of, N));
+    CKC(dmalloc(&h->d_status, N)); CKC(dmalloc(&h->d_llr_grid, N * 174)); CKC(dmalloc(&h->d_grid_sd, N)); CKC(dmalloc(&h->d_grid_snr, N));
+    CKC(dmalloc(&h->d_llr_fine, N * 174)); CKC(dmalloc(&h->d_fine, N)); CKC(dmalloc(&h->d_saved, N * 5 * 174));
+    CKC(dmalloc(&h->d_saved_n, N)); CKC(dmalloc(&h->d_saved_ap, N * 5)); CKC(dmalloc(&h->d_bits, N * 3));
+    CKC(dmalloc(&h->d_ripass, N)); CKC(dmalloc(&h->d_rap, N)); CKC(dmalloc(&h->d_rmethod, N)); CKC(dmalloc(&h->d_rnits, N));
+    CKC(dmalloc(&h->d_osd_found, N * 10)); CKC(dmalloc(&h->d_osd_bits, N * 30));
+    CKC(dmalloc(&h->d_list_fine, N)); CKC(dmalloc(&h->d_list_osd, N)); CKC(dmalloc(&h->d_counts, 4));
+    CKC(dmalloc(&h->d_stats, 1)); CKC(dmalloc(&h->d_rec, N));
+    CKC(cudaMallocHost((void**)&h->h_rec, N * sizeof(ft8_record)));
+    CKC(cudaMallocHost((void**)&h->h_counts, 4 * sizeof(int32_t)));
+    CKC(cudaMallocHost((void**)&h->h_stats, sizeof(DevStats)));
+    {
+        std::vector<int32_t> co(N);
+        for (size_t i = 0; i < N; ++i) co[i] = (int32_t)(i / K);
+        CKC(cudaMemcpy(h->d_cycle_of, co.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    CKC(cudaFuncSetAttribute(k_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, FINE_SMEM_BYTES));
+    CKC(cudaFuncSetAttribute(k_spectrogram<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_ROWS * 1920 * (int)sizeof(float2)));
+    CKC(cudaFuncSetAttribute(k_spectrogram<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_ROWS * 1920 * (int)sizeof(float2)));
+    CKC(cudaFuncSetAttribute(k_sync_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
+    CKC(cudaDeviceSynchronize());
+#undef CKC
+    *out = h;
+    return FT8_OK;
+}
+
+extern "C" void ft8_destroy(ft8_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {h->d_hann, h->d_W1920, h->d_W3840, h->d_W3200, h->d_W375, h->d_W256, h->d_W96000, h->d_W192000, h->d_W32,
+                    h->d_pulse, h->d_audio, h->d_grid, h->d_Y, h->d_spec, h->d_best_score, h->d_best_h0, h->d_f0, h->d_h0, h->d_score,
+                    h->d_ncand, h->d_cycle_of, h->d_status, h->d_llr_grid, h->d_grid_sd, h->d_grid_snr, h->d_llr_fine, h->d_fine,
+                    h->d_saved, h->d_saved_n, h->d_saved_ap, h->d_bits, h->d_ripass, h->d_rap, h->d_rmethod, h->d_rnits,
+                    h->d_osd_found, h->d_osd_bits, h->d_list_fine, h->d_list_osd, h->d_counts, h->d_stats, h->d_rec, h->arena};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->h_rec) cudaFreeHost(h->h_rec);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char* ft8_last_error(ft8_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+extern "C" void* ft8_stream(ft8_handle* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int ft8_synchronize(ft8_handle* h) {
+    if (!h) return FT8_E_BADARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return FT8_OK;
+}
+extern "C" int ft8_get_stats(ft8_handle* h, ft8_stats* out) {
+    if (!h || !out) return FT8_E_BADARG;
+    *out = h->stats;
+    return FT8_OK;
+}
+extern "C" int ft8_last_kernel_ms(ft8_handle* h, int which, float* ms) {
+    if (!h || !ms || which < 0 || which > 2) return FT8_E_BADARG;
+    *ms = h->last_ms[which];
+    return FT8_OK;
+}
+
+// ------------------------------------------------------------------------------------------ launch helpers
+static CandState cand_state(ft8_handle* h) {
+    CandState cs;
+    cs.K = h->cfg.max_cands; cs.n_cand = h->d_ncand; cs.f0 = h->d_f0; cs.h0 = h->d_h0; cs.score = h->d_score;
+    cs.status = h->d_status; cs.llr_grid = h->d_llr_grid; cs.grid_sd = h->d_grid_sd; cs.grid_snr = h->d_grid_snr;
+    cs.llr_fine = h->d_llr_fine; cs.fine = h->d_fine; cs.saved_llr = h->d_saved; cs.saved_n = h->d_saved_n;
+    cs.saved_ap = h->d_saved_ap; cs.bits91 = h->d_bits; cs.r_ipass = h->d_ripass; cs.r_ap = h->d_rap;
+    cs.r_method = h->d_rmethod; cs.r_nits = h->d_rnits; cs.osd_found = h->d_osd_found; cs.osd_bits = h->d_osd_bits;
+    return cs;
+}
+
+static int launch_spectrogram(ft8_handle* h, const void* d_audio, int dtype, int B, float* d_grid) {
+    dim3 grid((375 + SP_ROWS - 1) / SP_ROWS, B);
+    const int smem = SP_ROWS * 1920 * (int)sizeof(float2);
+    if (dtype == FT8_AUDIO_I16)
+        k_spectrogram<int16_t><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const int16_t*)d_audio, d_grid, h->d_hann, h->d_W1920, h->d_W3840);
+    else
+        k_spectrogram<float><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const float*)d_audio, d_grid, h->d_hann, h->d_W1920, h->d_W3840);
+    CK(cudaGetLastError());
+    return FT8_OK;
+}
+
+static int launch_sync(ft8_handle* h, const float* d_grid, int grid_rows, int B, int odd_even) {
+    const int cycle_h0 = odd_even ? 375 : 0;
+    k_sync_scores<<<dim3(N_F0 / SY_TF, B), SY_NT, SY_SMEM_BYTES, h->stream>>>(d_grid, grid_rows, cycle_h0, h->d_best_score, h->d_best_h0);
+    CK(cudaGetLastError());
+    k_topk<<<B, 960, 0, h->stream>>>(h->d_best_score, h->d_best_h0, h->cfg.sync_score_min, h->cfg.max_cands, h->d_f0, h->d_h0,
+                                     h->d_score, h->d_ncand);
+    CK(cudaGetLastError());
+    return FT8_OK;
+}
+
+// cycle spectra for B cycles into spec[B][stride], processed in chunks bounded by the Y scratch
+static int launch_cycle_spectrum(ft8_handle* h, const void* d_audio, int dtype, int B, float2* d_spec, int stride, int kmax) {
+    const size_t esz = dtype == FT8_AUDIO_I16 ? 2 : 4;
+    for (int b0 = 0; b0 < B; b0 += (int)h->y_cycles) {
+        const int nb = std::min<int>((int)h->y_cycles, B - b0);
+        const char* a = (const char*)d_audio + (size_t)b0 * CYCLE_SAMPLES * esz;
+        const int smem = CS_COLS * CS_N1 * (int)sizeof(float2);
+        if (dtype == FT8_AUDIO_I16)
+            k_cs_cols<int16_t><<<dim3(CS_N2 / CS_COLS, nb), CS_NT, smem, h->stream>>>((const int16_t*)a, h->d_Y, h->d_W375, h->d_W96000);
+        else
+            k_cs_cols<float><<<dim3(CS_N2 / CS_COLS, nb), CS_NT, smem, h->stream>>>((const float*)a, h->d_Y, h->d_W375, h->d_W96000);
+        CK(cudaGetLastError());
+        k_cs_rows<<<dim3(24, nb), CS_NT, 0, h->stream>>>(h->d_Y, d_spec + (size_t)b0 * stride, stride, kmax, h->d_W256, h->d_W192000);
+        CK(cudaGetLastError());
+    }
+    return FT8_OK;
+}
+
+static int persistent_blocks(ft8_handle* h, int per_sm) { return h->n_sm * per_sm; }
+
+// copy helpers honouring the mem flag
+static int to_device(ft8_handle* h, void* d, const void* src, size_t bytes, int mem) {
+    CK(cudaMemcpyAsync(d, src, bytes, mem == FT8_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+    return FT8_OK;
+}
+static int from_device(ft8_handle* h, void* dst, const void* d, size_t bytes, int mem) {
+    CK(cudaMemcpyAsync(dst, d, bytes, mem == FT8_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+    return FT8_OK;
+}
+
+#define ENTER(h)                                  \
+    if (!(h)) return FT8_E_BADARG;                \
+    CK(cudaSetDevice((h)->device));
+#define TRY(x) do { int r__ = (x); if (r__ != FT8_OK) return r__; } while (0)
+
+static int stage_audio(ft8_handle* h, const void* audio, int dtype, int B, int mem, const void** d_audio) {
+    if (dtype != FT8_AUDIO_I16 && dtype != FT8_AUDIO_F32) return fail(h, FT8_E_BADARG, "audio_dtype must be FT8_AUDIO_I16 or FT8_AUDIO_F32");
+    if (mem == FT8_MEM_DEVICE) { *d_audio = audio; return FT8_OK; }
+    const size_t bytes = (size_t)B * CYCLE_SAMPLES * (dtype == FT8_AUDIO_I16 ? 2 : 4);
+    TRY(ensure_audio(h, bytes));
+    TRY(to_device(h, h->d_audio, audio, bytes, mem));
+    *d_audio = h->d_audio;
+    return FT8_OK;
+}
+
+// ------------------------------------------------------------------------------------------ stage ops
+extern "C" int ft8_spectrogram(ft8_handle* h, const void* audio, int audio_dtype, int B, float* grid_db, int mem) {
+    ENTER(h);
+    if (!audio || !grid_db || B <= 0) return fail(h, FT8_E_BADARG, "ft8_spectrogram: bad argument");
+    if ((size_t)B > h->cap_cycles) return fail(h, FT8_E_CAPACITY, "ft8_spectrogram: B exceeds cfg.max_cycles");
+    const void* da;
+    TRY(stage_audio(h, audio, audio_dtype, B, mem, &da));
+    float* dg = mem == FT8_MEM_DEVICE ? grid_db : h->d_grid;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    TRY(launch_spectrogram(h, da, audio_dtype, B, dg));
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    if (mem == FT8_MEM_HOST) TRY(from_device(h, grid_db, dg, (size_t)B * GRID_ROWS * GRID_COLS * sizeof(float), mem));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->last_ms[1], h->ev[0], h->ev[1]));
+    return FT8_OK;
+}
+
+extern "C" int ft8_sync(ft8_handle* h, const float* grid_db, int grid_rows, int B, int odd_even, int16_t* cand_f0,
+                        int16_t* cand_h0, float* cand_score, int32_t* n_cand, float* payload_db, int mem) {
+    ENTER(h);
+    if (!grid_db || !cand_f0 || !cand_h0 || !cand_score || !n_cand || B <= 0) return fail(h, FT8_E_BADARG, "ft8_sync: bad argument");
+    if (grid_rows != GRID_ROWS && grid_rows != LIVE_ROWS) return fail(h, FT8_E_BADARG, "ft8_sync: grid_rows must be 376 or 750");
+    if ((size_t)B > h->cap_cycles) return fail(h, FT8_E_CAPACITY, "ft8_sync: B exceeds cfg.max_cycles");
+    const size_t K = h->cfg.max_cands, N = (size_t)B * K;
+    const float* dg = grid_db;
+    if (mem == FT8_MEM_HOST) {
+        const size_t bytes = (size_t)B * grid_rows * GRID_COLS * sizeof(float);
+        if (grid_rows == GRID_ROWS) { TRY(to_device(h, h->d_grid, grid_db, bytes, mem)); dg = h->d_grid; }
+        else { TRY(ensure_arena(h, bytes)); TRY(to_device(h, h->arena, grid_db, bytes, mem)); dg = (const float*)h->arena; }
+    }
+    CK(cudaMemsetAsync(h->d_f0, 0, N * 2, h->stream));
+    CK(cudaMemsetAsync(h->d_h0, 0, N * 2, h->stream));
+    CK(cudaMemsetAsync(h->d_score, 0, N * 4, h->stream));
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    TRY(launch_sync(h, dg, grid_rows, B, odd_even));
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    float* d_pay = nullptr;
+    if (payload_db) {
+        if (mem == FT8_MEM_DEVICE) d_pay = payload_db;
+        else {
+            // the arena may hold the live grid: place the payload scratch after it
+            const size_t gbytes = (grid_rows == GRID_ROWS) ? 0 : (size_t)B * grid_rows * GRID_COLS * sizeof(float);
+            if (gbytes) return fail(h, FT8_E_BADARG, "ft8_sync: payload_db with a host 750-row grid is not supported; pass grid_rows=376 or device memory");
+            TRY(ensure_arena(h, N * 58 * 8 * sizeof(float)));
+            d_pay = (float*)h->arena;
+        }
+        CK(cudaMemsetAsync(d_pay, 0, N * 58 * 8 * sizeof(float), h->stream));
+        CK(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), h->stream));
+        k_pass0<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
+            cand_state(h), (int)N, dg, grid_rows, odd_even ? 375 : 0, h->cfg.llr_sd_min, d_pay, 1, h->d_list_fine, h->d_counts, h->d_stats);
+        CK(cudaGetLastError());
+    }
+    TRY(from_device(h, cand_f0, h->d_f0, N * 2, mem));
+    TRY(from_device(h, cand_h0, h->d_h0, N * 2, mem));
+    TRY(from_device(h, cand_score, h->d_score, N * 4, mem));
+    TRY(from_device(h, n_cand, h->d_ncand, (size_t)B * 4, mem));
+    if (payload_db && mem == FT8_MEM_HOST) TRY(from_device(h, payload_db, d_pay, N * 58 * 8 * sizeof(float), mem));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->last_ms[2], h->ev[2], h->ev[3]));
+    return FT8_OK;
+}
+
+// carve typed sub-buffers out of the arena
+struct Carver {
+    char* base; size_t off = 0;
+    template <typename T> T* take(size_t n) { off = (off + 255) & ~(size_t)255; T* p = (T*)(base + off); off += n * sizeof(T); return p; }
+};
+
+extern "C" int ft8_llr(ft8_handle* h, const float* payload_db, int N, float* llr, float* sd, int32_t* snr, int mem) {
+    ENTER(h);
+    if (!payload_db || !llr || !sd || !snr || N <= 0) return fail(h, FT8_E_BADARG, "ft8_llr: bad argument");
+    const float* dp = payload_db; float* dl = llr; float* ds = sd; int32_t* dn = snr;
+    if (mem == FT8_MEM_HOST) {
+        TRY(ensure_arena(h, (size_t)N * (464 + 174 + 2) * 4 + 4096));
+        Carver c{(char*)h->arena};
+        float* p = c.take<float>((size_t)N * 464); dl = c.take<float>((size_t)N * 174); ds = c.take<float>(N); dn = c.take<int32_t>(N);
+        TRY(to_device(h, p, payload_db, (size_t)N * 464 * 4, mem));
+        dp = p;
+    }
+    k_llr_batch<<<std::min(persistent_blocks(h, 8), (N + WARPS_PER_CTA - 1) / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, h->stream>>>(dp, N, dl, ds, dn);
+    CK(cudaGetLastError());
+    if (mem == FT8_MEM_HOST) {
+        TRY(from_device(h, llr, dl, (size_t)N * 174 * 4, mem));
+        TRY(from_device(h, sd, ds, (size_t)N * 4, mem));
+        TRY(from_device(h, snr, dn, (size_t)N * 4, mem));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return FT8_OK;
+}
+
+extern "C" int ft8_cycle_spectrum(ft8_handle* h, const void* audio, int audio_dtype, int B, float* spec, int mem) {
+    ENTER(h);
+    if (!audio || !spec || B <= 0) return fail(h, FT8_E_BADARG, "ft8_cycle_spectrum: bad argument");
+    if ((size_t)B > h->cap_cycles) return fail(h, FT8_E_CAPACITY, "ft8_cycle_spectrum: B exceeds cfg.max_cycles");
+    const void* da;
+    TRY(stage_audio(h, audio, audio_dtype, B, mem, &da));
+    float2* ds = (float2*)spec;
+    if (mem == FT8_MEM_HOST) { TRY(ensure_arena(h, (size_t)B * FT8_SPEC_BINS * sizeof(float2))); ds = (float2*)h->arena; }
+    TRY(launch_cycle_spectrum(h, da, audio_dtype, B, ds, FT8_SPEC_BINS, FT8_SPEC_BINS - 1));
+    if (mem == FT8_MEM_HOST) TRY(from_device(h, spec, ds, (size_t)B * FT8_SPEC_BINS * sizeof(float2), mem));
+    CK(cudaStreamSynchronize(h->stream));
+    return FT8_OK;
+}
+
+extern "C" int ft8_fine(ft8_handle* h, const float* spec, int B, const int32_t* cycle_of, const int16_t* f0_idx,
+                        const int16_t* h0_idx, int N, int32_t* ttweak, int32_t* ftweak, int32_t* nsync, float* signal_grid,
+                        float* llr, float* sd, int32_t* snr, int mem) {
+    ENTER(h);
+    if (!spec || !cycle_of || !f0_idx || !h0_idx || !ttweak || !ftweak || !nsync || !llr || !sd || !snr || N <= 0 || B <= 0)
+        return fail(h, FT8_E_BADARG, "ft8_fine: bad argument");
+    const size_t specn = (size_t)B * FT8_SPEC_BINS;
+    size_t need = specn * 8 + (size_t)N * (4 + 2 + 2 + sizeof(FineOut) + 174 * 4 + 632 * 4) + 8 * 256;
+    TRY(ensure_arena(h, need));
+    Carver c{(char*)h->arena};
+    float2* dspec = c.take<float2>(specn);
+    int32_t* dco = c.take<int32_t>(N); int16_t* df0 = c.take<int16_t>(N); int16_t* dh0 = c.take<int16_t>(N);
+    FineOut* dfo = c.take<FineOut>(N); float* dllr = c.take<float>((size_t)N * 174); float* dsg = c.take<float>((size_t)N * 632);
+    const float2* sp = (const float2*)spec;
+    if (mem == FT8_MEM_HOST) { TRY(to_device(h, dspec, spec, specn * 8, mem)); sp = dspec; }
+    TRY(to_device(h, dco, cycle_of, (size_t)N * 4, mem));
+    TRY(to_device(h, df0, f0_idx, (size_t)N * 2, mem));
+    TRY(to_device(h, dh0, h0_idx, (size_t)N * 2, mem));
+    k_fine<<<std::min(persistent_blocks(h, 4), N), FINE_NT, FINE_SMEM_BYTES, h->stream>>>(
+        sp, FT8_SPEC_BINS, nullptr, nullptr, N, dco, df0, dh0, h->d_W3200, dfo, dllr, signal_grid ? dsg : nullptr);
+    CK(cudaGetLastError());
+    std::vector<FineOut> fo(N);
+    CK(cudaMemcpyAsync(fo.data(), dfo, (size_t)N * sizeof(FineOut), cudaMemcpyDeviceToHost, h->stream));
+    TRY(from_device(h, llr, dllr, (size_t)N * 174 * 4, mem));
+    if (signal_grid) TRY(from_device(h, signal_grid, dsg, (size_t)N * 632 * 4, mem));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<int32_t> t(N), f(N), ns(N), sn(N);
+    std::vector<float> s(N);
+    for (int i = 0; i < N; ++i) { t[i] = fo[i].tt; f[i] = fo[i].ff; ns[i] = fo[i].nsync; s[i] = fo[i].sd; sn[i] = fo[i].snr; }
+    const cudaMemcpyKind kind = mem == FT8_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice;
+    CK(cudaMemcpy(ttweak, t.data(), (size_t)N * 4, kind)); CK(cudaMemcpy(ftweak, f.data(), (size_t)N * 4, kind));
+    CK(cudaMemcpy(nsync, ns.data(), (size_t)N * 4, kind)); CK(cudaMemcpy(sd, s.data(), (size_t)N * 4, kind));
+    CK(cudaMemcpy(snr, sn.data(), (size_t)N * 4, kind));
+    return FT8_OK;
+}
+
+extern "C" int ft8_ldpc(ft8_handle* h, float* llr, int N, int max_ncheck0, int max_iters, int32_t* status, int32_t* nits,
+                        uint32_t* bits91, int mem) {
+    ENTER(h);
+    if (!llr || !status || !nits || !bits91 || N <= 0 || max_iters < 0) return fail(h, FT8_E_BADARG, "ft8_ldpc: bad argument");
+    float* dl = llr; int32_t* dst = status; int32_t* dn = nits; uint32_t* db = bits91;
+    if (mem == FT8_MEM_HOST) {
+        TRY(ensure_arena(h, (size_t)N * (174 + 1 + 1 + 3) * 4 + 4096));
+        Carver c{(char*)h->arena};
+        dl = c.take<float>((size_t)N * 174); dst = c.take<int32_t>(N); dn = c.take<int32_t>(N); db = c.take<uint32_t>((size_t)N * 3);
+        TRY(to_device(h, dl, llr, (size_t)N * 174 * 4, mem));
+    }
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    k_ldpc_batch<<<std::min(persistent_blocks(h, 8), (N + WARPS_PER_CTA - 1) / WARPS_PER_CTA), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
+        dl, N, max_ncheck0, max_iters, dst, dn, db);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[5], h->stream));
+    if (mem == FT8_MEM_HOST) {
+        TRY(from_device(h, llr, dl, (size_t)N * 174 * 4, mem));
+        TRY(from_device(h, status, dst, (size_t)N * 4, mem));
+        TRY(from_device(h, nits, dn, (size_t)N * 4, mem));
+        TRY(from_device(h, bits91, db, (size_t)N * 12, mem));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[4], h->ev[5]));
+    return FT8_OK;
+}
+
+extern "C" int ft8_osd(ft8_handle* h, const float* llr, int N, int singleflips, int doubleflips, int32_t* found,
+                       uint32_t* bits91, int mem) {
+    ENTER(h);
+    if (!llr || !found || !bits91 || N <= 0 || singleflips < 0 || singleflips > OSD_MAX_FLIPS || doubleflips < 0)
+        return fail(h, FT8_E_BADARG, "ft8_osd: bad argument (singleflips must be 0..91)");
+    const float* dl = llr; int32_t* df = found; uint32_t* db = bits91;
+    if (mem == FT8_MEM_HOST) {
+        TRY(ensure_arena(h, (size_t)N * (174 + 1 + 3) * 4 + 4096));
+        Carver c{(char*)h->arena};
+        float* l = c.take<float>((size_t)N * 174); df = c.take<int32_t>(N); db = c.take<uint32_t>((size_t)N * 3);
+        TRY(to_device(h, l, llr, (size_t)N * 174 * 4, mem));
+        dl = l;
+    }
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    k_osd_batch<<<std::min(persistent_blocks(h, 8), (N + WARPS_PER_CTA - 1) / WARPS_PER_CTA), WARPS_PER_CTA * 32, sizeof(OsdSmem), h->stream>>>(
+        dl, N, singleflips, doubleflips, df, db);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[5], h->stream));
+    if (mem == FT8_MEM_HOST) {
+        TRY(from_device(h, found, df, (size_t)N * 4, mem));
+        TRY(from_device(h, bits91, db, (size_t)N * 12, mem));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[4], h->ev[5]));
+    return FT8_OK;
+}
+
+extern "C" int ft8_crc14(ft8_handle* h, const uint32_t* bits91, int N, int32_t* flags, int mem) {
+    ENTER(h);
+    if (!bits91 || !flags || N <= 0) return fail(h, FT8_E_BADARG, "ft8_crc14: bad argument");
+    const uint32_t* db = bits91; int32_t* df = flags;
+    if (mem == FT8_MEM_HOST) {
+        TRY(ensure_arena(h, (size_t)N * 16 + 4096));
+        Carver c{(char*)h->arena};
+        uint32_t* b = c.take<uint32_t>((size_t)N * 3); df = c.take<int32_t>(N);
+        TRY(to_device(h, b, bits91, (size_t)N * 12, mem));
+        db = b;
+    }
+    k_crc_batch<<<std::min(persistent_blocks(h, 8), (N + 127) / 128), 128, 0, h->stream>>>(db, N, df);
+    CK(cudaGetLastError());
+    if (mem == FT8_MEM_HOST) TRY(from_device(h, flags, df, (size_t)N * 4, mem));
+    CK(cudaStreamSynchronize(h->stream));
+    return FT8_OK;
+}
+
+// ------------------------------------------------------------------------------------------ whole path
+__global__ void k_collect(CandState cs, int n_slots, FineOut* __restrict__ fine, ft8_record* __restrict__ rec, int32_t* __restrict__ n_rec) {
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += gridDim.x * blockDim.x) {
+        const int cyc = slot / cs.K, rank = slot - cyc * cs.K;
+        if (rank >= cs.n_cand[cyc] || cs.status[slot] != ST_DECODED) continue;
+        ft8_record r;
+        memset(&r, 0, sizeof(r));
+        r.bits91[0] = cs.bits91[3 * slot]; r.bits91[1] = cs.bits91[3 * slot + 1]; r.bits91[2] = cs.bits91[3 * slot + 2];
+        r.cycle = cyc; r.cand = (int16_t)rank; r.f0_idx = cs.f0[slot]; r.h0_idx = cs.h0[slot];
+        r.ipass = cs.r_ipass[slot]; r.ap = cs.r_ap[slot]; r.method = cs.r_method[slot]; r.n_its = cs.r_nits[slot];
+        r.score = cs.score[slot]; r.grid_sd = cs.grid_sd[slot];
+        // float(h0/25) and 3.125*f0 like receiver.py:350-351 (python floats; rounded to fp32 for the record)
+        double tsec = (double)r.h0_idx / 25.0, fhz = 3.125 * (double)r.f0_idx;
+        if (r.ipass >= 2) {
+            const FineOut fo = fine[slot];
+            r.ttweak = (int8_t)fo.tt; r.ftweak = (int8_t)fo.ff; r.nsync = (uint8_t)fo.nsync; r.fine_sd = fo.sd; r.snr = (int8_t)fo.snr;
+            tsec += (double)fo.tt / 200.0; fhz += (double)fo.ff / 16.0;
+        } else {
+            r.nsync = 100; r.fine_sd = nanf(""); r.snr = cs.grid_snr[slot];
+        }
+        r.tsec = (float)tsec; r.fHz = (float)fhz;
+        rec[atomicAdd(n_rec, 1)] = r;
+    }
+}
+
+extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even, ft8_record* rec,
+                                 int rec_capacity, int32_t* n_rec, int mem) {
+    ENTER(h);
+    if (!audio || !rec || !n_rec || B <= 0 || rec_capacity < 0) return fail(h, FT8_E_BADARG, "ft8_decode_cycles: bad argument");
+    if ((size_t)B > h->cap_cycles) return fail(h, FT8_E_CAPACITY, "ft8_decode_cycles: B exceeds cfg.max_cycles");
+    const int K = h->cfg.max_cands, N = B * K;
+    const int cycle_h0 = odd_even ? 375 : 0;
+    const void* da;
+    TRY(stage_audio(h, audio, audio_dtype, B, mem, &da));
+    int launches = 0;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    CK(cudaMemsetAsync(h->d_counts, 0, 4 * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), h->stream));
+    // S1
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    TRY(launch_spectrogram(h, da, audio_dtype, B, h->d_grid)); ++launches;
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    // S2
+    TRY(launch_sync(h, h->d_grid, GRID_ROWS, B, odd_even)); launches += 2;
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    // F1 (independent of S1/S2; same stream for now)
+    TRY(launch_cycle_spectrum(h, da, audio_dtype, B, h->d_spec, FINE_SPEC_STRIDE, FINE_SPEC_STRIDE - 1));
+    launches += 2 * ((B + (int)h->y_cycles - 1) / (int)h->y_cycles);
+    CandState cs = cand_state(h);
+    // ipass 0
+    k_pass0<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
+        cs, N, h->d_grid, GRID_ROWS, cycle_h0, h->cfg.llr_sd_min, nullptr, 0, h->d_list_fine, h->d_counts + 0, h->d_stats);
+    CK(cudaGetLastError()); ++launches;
+    // ipass 1
+    k_fine<<<persistent_blocks(h, 4), FINE_NT, FINE_SMEM_BYTES, h->stream>>>(
+        h->d_spec, FINE_SPEC_STRIDE, h->d_list_fine, h->d_counts + 0, 0, h->d_cycle_of, h->d_f0, h->d_h0, h->d_W3200, h->d_fine,
+        h->d_llr_fine, nullptr);
+    CK(cudaGetLastError()); ++launches;
+    // ipass 2-4
+    k_pass234<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
+        cs, h->d_list_fine, h->d_counts + 0, h->cfg.llr_sd_min, h->d_list_osd, h->d_counts + 1, h->d_stats);
+    CK(cudaGetLastError()); ++launches;
+    // ipass 5-6
+    k_osd_items<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(OsdSmem), h->stream>>>(
+        cs, h->d_list_osd, h->d_counts + 1, h->cfg.osd_singleflips, h->cfg.osd_doubleflips, h->d_stats);
+    CK(cudaGetLastError()); ++launches;
+    k_osd_resolve<<<persistent_blocks(h, 2), 128, 0, h->stream>>>(cs, h->d_list_osd, h->d_counts + 1, h->d_stats);
+    CK(cudaGetLastError()); ++launches;
+    k_collect<<<persistent_blocks(h, 4), 256, 0, h->stream>>>(cs, N, h->d_fine, h->d_rec, h->d_counts + 2);
+    CK(cudaGetLastError()); ++launches;
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaMemcpyAsync(h->h_counts, h->d_counts, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const int nrec = h->h_counts[2];
+    if (nrec > 0) {
+        CK(cudaMemcpyAsync(h->h_rec, h->d_rec, (size_t)nrec * sizeof(ft8_record), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]));
+    CK(cudaEventElapsedTime(&h->last_ms[1], h->ev[2], h->ev[3]));
+    CK(cudaEventElapsedTime(&h->last_ms[2], h->ev[3], h->ev[4]));
+    // emission order (receiver.py:389-398): pass by pass; inside a pass by llr_sd descending (the fine sd from
+    // ipass 2 on, all-equal before), ties by candidate rank; then de-dup on the payload (receiver.py:53-55)
+    std::sort(h->h_rec, h->h_rec + nrec, [](const ft8_record& a, const ft8_record& b) {
+        if (a.cycle != b.cycle) return a.cycle < b.cycle;
+        if (a.ipass != b.ipass) return a.ipass < b.ipass;
+        if (a.ipass >= 2 && a.fine_sd != b.fine_sd) return a.fine_sd > b.fine_sd;
+        return a.cand < b.cand;
+    });
+    for (int b = 0; b < B; ++b) n_rec[b] = 0;
+    int64_t emitted = 0;
+    int written = 0, i = 0;
+    bool overflow = false;
+    while (i < nrec) {
+        int j = i;
+        while (j < nrec && h->h_rec[j].cycle == h->h_rec[i].cycle) ++j;
+        for (int a = i; a < j; ++a) {
+            ft8_record& r = h->h_rec[a];
+            r.emitted = 1;
+            for (int c = i; c < a; ++c) {
+                const ft8_record& q = h->h_rec[c];
+                if (q.bits91[0] == r.bits91[0] && q.bits91[1] == r.bits91[1] && ((q.bits91[2] ^ r.bits91[2]) & 0x1FFFu) == 0) { r.emitted = 0; break; }
+            }
+            emitted += r.emitted;
+            if (written < rec_capacity) { rec[written++] = r; n_rec[r.cycle]++; } else overflow = true;
+        }
+        i = j;
+    }
+    ft8_stats& s = h->stats;
+    memset(&s, 0, sizeof(s));
+    s.cycles = B; s.candidates = (int64_t)h->h_stats->candidates; s.stopped_sd = (int64_t)h->h_stats->stopped_sd;
+    s.fine_evals = (int64_t)h->h_stats->fine_evals; s.fine_pass = (int64_t)h->h_stats->fine_pass;
+    s.ldpc_calls = (int64_t)h->h_stats->ldpc_calls; s.ldpc_iters = (int64_t)h->h_stats->ldpc_iters;
+    s.osd_calls = (int64_t)h->h_stats->osd_calls; s.decoded = nrec; s.emitted = emitted; s.kernel_launches = launches;
+    if (overflow) return fail(h, FT8_E_CAPACITY, "ft8_decode_cycles: rec_capacity too small (records truncated)");
+    return FT8_OK;
+}
+
+// ------------------------------------------------------------------------------------------ generator + test hook
+extern "C" int ft8_synth_cycles(ft8_handle* h, const uint8_t* symbols, const float* f_hz, const float* dt_s, const float* amp,
+                                int B, int n_sig, float noise_sigma, uint64_t seed, int16_t* audio, int mem) {
+    ENTER(h);
+    if (!symbols || !f_hz || !dt_s || !amp || !audio || B <= 0 || n_sig < 0 || n_sig > SYNTH_MAX_SIG)
+        return fail(h, FT8_E_BADARG, "ft8_synth_cycles: bad argument (n_sig <= 128)");
+    const size_t ns = (size_t)B * n_sig;
+    TRY(ensure_arena(h, ns * (79 + 12) + (mem == FT8_MEM_HOST ? (size_t)B * CYCLE_SAMPLES * 2 : 0) + 4096));
+    Carver c{(char*)h->arena};
+    uint8_t* dsym = c.take<uint8_t>(ns * 79); float* df = c.take<float>(ns); float* dd = c.take<float>(ns); float* dam = c.take<float>(ns);
+    int16_t* da = mem == FT8_MEM_HOST ? c.take<int16_t>((size_t)B * CYCLE_SAMPLES) : audio;
+    // parameters are small and always come from the host
+    CK(cudaMemcpyAsync(dsym, symbols, ns * 79, cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(df, f_hz, ns * 4, cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(dd, dt_s, ns * 4, cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(dam, amp, ns * 4, cudaMemcpyDefault, h->stream));
+    k_synth<<<dim3((CYCLE_SAMPLES + SYNTH_TILE - 1) / SYNTH_TILE, B), SYNTH_NT, 0, h->stream>>>(dsym, df, dd, dam, n_sig, noise_sigma, seed, h->d_pulse, da);
+    CK(cudaGetLastError());
+    if (mem == FT8_MEM_HOST) TRY(from_device(h, audio, da, (size_t)B * CYCLE_SAMPLES * 2, mem));
+    CK(cudaStreamSynchronize(h->stream));
+    return FT8_OK;
+}
+
+template <int N, int NT, bool INV>
+__global__ void k_debug_fft(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ W) {
+    extern __shared__ float2 dbg_smem[];
+    const float2* x = in + (size_t)blockIdx.x * N;
+    for (int i = threadIdx.x; i < N; i += NT) dbg_smem[i] = x[i];
+    __syncthreads();
+    if (N == 1920) fft1920<NT, INV>(dbg_smem, threadIdx.x, W);
+    if (N == 3200) fft3200<NT, INV>(dbg_smem, threadIdx.x, W);
+    if (N == 375) fft375<NT, INV>(dbg_smem, threadIdx.x, W);
+    if (N == 256) fft256<NT, INV>(dbg_smem, threadIdx.x, W);
+    if (N == 32) fft32<NT, INV>(dbg_smem, threadIdx.x, W);
+    for (int i = threadIdx.x; i < N; i += NT) out[(size_t)blockIdx.x * N + i] = dbg_smem[i];
+}
+
+extern "C" int ft8_debug_fft(ft8_handle* h, int n, int inverse, const float* in, float* out, int batch) {
+    ENTER(h);
+    if (!in || !out || batch <= 0) return fail(h, FT8_E_BADARG, "ft8_debug_fft: bad argument");
+    const size_t bytes = (size_t)batch * n * sizeof(float2);
+    TRY(ensure_arena(h, 2 * bytes + 512));
+    Carver c{(char*)h->arena};
+    float2* di = c.take<float2>((size_t)batch * n); float2* dout = c.take<float2>((size_t)batch * n);
+    TRY(to_device(h, di, in, bytes, FT8_MEM_HOST));
+#define DBG(NN, NT, WT)                                                                                                    \
+    if (n == NN) {                                                                                                         \
+        if (inverse) k_debug_fft<NN, NT, true><<<batch, NT, NN * sizeof(float2), h->stream>>>(di, dout, WT);               \
+        else k_debug_fft<NN, NT, false><<<batch, NT, NN * sizeof(float2), h->stream>>>(di, dout, WT);                      \
+    }
+    DBG(1920, 128, h->d_W1920) else DBG(3200, 256, h->d_W3200) else DBG(375, 128, h->d_W375) else DBG(256, 64, h->d_W256)
+    else DBG(32, 32, h->d_W32) else return fail(h, FT8_E_BADARG, "ft8_debug_fft: n must be 32, 256, 375, 1920 or 3200");
+#undef DBG
+    CK(cudaGetLastError());
+    TRY(from_device(h, out, dout, bytes, FT8_MEM_HOST));
+    CK(cudaStreamSynchronize(h->stream));
+    return FT8_OK;
+}

@@ -1,0 +1,195 @@
+// osd.cuh -- ordered-statistics decoding (order 0 + single/double flips), one warp per codeword.
+//
+// Restates osd_012 (decoders.py:223-272).  The reference runs Gauss-Jordan on a
+// 91x174 uint8 matrix with row/column permutation lists.  Here the matrix is held COLUMN-major,
+// bit-packed: a column is the 91-bit vector of its entries over the rows (3 x u32), so
+//   * the initial matrix G0 = [I | A^T] needs no build step: column c < 91 is the unit vector
+//     e_c and column 91+i is generator row i (constant table c_osd.col);
+//   * columns are visited in reliability order (|llr| descending, ties by ascending index,
+//     NaN last -- numpy's argsort(-|llr|) made stable); sorted position s lives in
+//     lane s%32, register slot s/32, so all register indices are compile-time;
+//   * a pivot step is: broadcast the column (3 shuffles), pick an unused row with a 1 (any such
+//     row gives the same reduced matrix -- the reduced form for a fixed pivot-column set is
+//     unique up to row order, and every result below is expressed through pivots, not row
+//     numbers), then every lane conditionally XORs the pivot column into its 6 columns;
+//   * T = G[:, :91] are the columns with original index < 91 wherever they sit;
+//     trial word bit c = parity(u & col_c) with u[row of pivot k] = hard[column of pivot k];
+//     flipping u at the row of pivot 90-i adds (row of T) = bit (row) of every col_c.
+// CRC-14 is linear, so each of the 1+S vectors carries its 14-bit syndrome and a trial's CRC test is an XOR.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "codec.cuh"
+
+namespace ft8 {
+
+struct OsdTables {
+    uint32_t col[174][3];      // column c of G0 over the 91 rows, LSB-first
+};
+__constant__ OsdTables c_osd;
+
+constexpr int OSD_MAX_FLIPS = 91;
+
+struct OsdWarpScratch {
+    unsigned long long key[176];     // sort keys
+    uint8_t perm[192];               // sorted position -> original column
+    uint8_t piv_row[96];             // pivot k -> row
+    uint32_t vec[OSD_MAX_FLIPS + 1][4];   // [0] = order-0 word, [1+i] = row of T for flip i; [..][3] = CRC syndrome
+};
+
+// Returns trial index + 1 of the first accepted trial word (0 = none); bits = that word.
+// llr: 174 floats in shared or global memory.
+__device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int lane, int S, int D, uint32_t* bits) {
+    // ---- 1. reliability order by rank counting
+    for (int i = lane; i < 174; i += 32) {
+        const float a = fabsf(llr[i]);
+        const uint32_t u = (a != a) ? 0u : (__float_as_uint(a) + 1u);       // NaN sorts last
+        s.key[i] = ((unsigned long long)u << 8) | (unsigned long long)(255 - i);
+    }
+    __syncwarp();
+    {
+        unsigned long long mine[6];
+        int rank[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const int i = lane + 32 * r;
+            mine[r] = (i < 174) ? s.key[i] : 0ull;
+            rank[r] = 0;
+        }
+        for (int j = 0; j < 174; ++j) {
+            const unsigned long long k = s.key[j];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) rank[r] += (k > mine[r]) ? 1 : 0;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const int i = lane + 32 * r;
+            if (i < 174) s.perm[rank[r]] = (uint8_t)i;
+        }
+    }
+    __syncwarp();
+    // ---- 2. load columns in sorted order; hard decisions per sorted position
+    uint32_t c0[6], c1[6], c2[6];
+    uint32_t hard_mask = 0;          // bit r: hard decision of this lane's slot r
+    uint32_t orig[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const int sp = lane + 32 * r;
+        if (sp < 174) {
+            const int c = s.perm[sp];
+            orig[r] = c;
+            c0[r] = c_osd.col[c][0]; c1[r] = c_osd.col[c][1]; c2[r] = c_osd.col[c][2];
+            if (llr[c] > 0.0f) hard_mask |= 1u << r;
+        } else {
+            orig[r] = 255; c0[r] = c1[r] = c2[r] = 0;
+        }
+    }
+    // ---- 3. Gauss-Jordan over columns in sorted order
+    uint32_t used0 = 0, used1 = 0, used2 = 0;     // rows already holding a pivot
+    uint32_t u0 = 0, u1 = 0, u2 = 0;              // u[row] = hard decision of that row's pivot column
+    int npiv = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        for (int l = 0; l < 32; ++l) {
+            if (npiv >= 91 || r * 32 + l >= 174) break;
+            const uint32_t v0 = __shfl_sync(0xffffffffu, c0[r], l);
+            const uint32_t v1 = __shfl_sync(0xffffffffu, c1[r], l);
+            const uint32_t v2 = __shfl_sync(0xffffffffu, c2[r], l);
+            const uint32_t f0 = v0 & ~used0, f1 = v1 & ~used1, f2 = v2 & ~used2;
+            if ((f0 | f1 | f2) == 0) continue;    // dependent column
+            int p;
+            if (f0) p = __ffs(f0) - 1; else if (f1) p = 32 + __ffs(f1) - 1; else p = 64 + __ffs(f2) - 1;
+            const uint32_t pb = 1u << (p & 31);
+            const int pw = p >> 5;
+            uint32_t m0 = v0, m1 = v1, m2 = v2;   // pivot column with the pivot row cleared
+            if (pw == 0) { m0 &= ~pb; used0 |= pb; } else if (pw == 1) { m1 &= ~pb; used1 |= pb; } else { m2 &= ~pb; used2 |= pb; }
+            const uint32_t hb = __shfl_sync(0xffffffffu, hard_mask >> r, l) & 1u;
+            if (hb) { if (pw == 0) u0 |= pb; else if (pw == 1) u1 |= pb; else u2 |= pb; }
+            if (lane == 0) s.piv_row[npiv] = (uint8_t)p;
+            ++npiv;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const uint32_t w = (pw == 0) ? c0[k] : ((pw == 1) ? c1[k] : c2[k]);
+                if (w & pb) { c0[k] ^= m0; c1[k] ^= m1; c2[k] ^= m2; }
+            }
+        }
+    }
+    __syncwarp();
+    // ---- 4. the 1+S vectors over the original columns 0..90, each with its CRC syndrome
+    const int nvec = 1 + S;
+    for (int vi = 0; vi < nvec; ++vi) {
+        uint32_t w0 = 0, w1 = 0, w2 = 0, syn = 0;
+        int prow = 0;
+        if (vi > 0) prow = s.piv_row[90 - (vi - 1)];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (orig[k] < 91) {
+                uint32_t b;
+                if (vi == 0) b = (__popc(c0[k] & u0) + __popc(c1[k] & u1) + __popc(c2[k] & u2)) & 1u;
+                else {
+                    const uint32_t w = (prow < 32) ? c0[k] : ((prow < 64) ? c1[k] : c2[k]);
+                    b = (w >> (prow & 31)) & 1u;
+                }
+                if (b) {
+                    const uint32_t c = orig[k];
+                    const uint32_t bit = 1u << (c & 31);
+                    if (c < 32) w0 |= bit; else if (c < 64) w1 |= bit; else w2 |= bit;
+                    syn ^= c_codec.crc_syn[c];
+                }
+            }
+        }
+        w0 = __reduce_or_sync(0xffffffffu, w0);
+        w1 = __reduce_or_sync(0xffffffffu, w1);
+        w2 = __reduce_or_sync(0xffffffffu, w2);
+        syn = __reduce_xor_sync(0xffffffffu, syn);
+        if (lane == 0) { s.vec[vi][0] = w0; s.vec[vi][1] = w1; s.vec[vi][2] = w2; s.vec[vi][3] = syn; }
+    }
+    __syncwarp();
+    // ---- 5. enumerate trials in the reference's order; first with payload != 0, CRC ok, valid payload
+    //      trial 0: base; 1..S: single flips i = 0..S-1; then pairs (i, j), j < D, j < i, i-major.
+    const int nsingle = S;
+    int npair = 0;
+    for (int i = 0; i < S; ++i) npair += min(i, D);
+    const int ntrial = 1 + nsingle + npair;
+    const uint32_t bs = s.vec[0][3];
+    for (int base = 0; base < ntrial; base += 32) {
+        const int tr = base + lane;
+        bool pass = false;
+        int fi = -1, fj = -1;
+        if (tr < ntrial) {
+            if (tr == 0) { }
+            else if (tr <= nsingle) fi = tr - 1;
+            else {
+                int q = tr - 1 - nsingle;      // q-th pair
+                int i = 0;
+                while (true) { const int cnt = min(i, D); if (q < cnt) break; q -= cnt; ++i; }
+                fi = i; fj = q;
+            }
+            uint32_t syn = bs;
+            if (fi >= 0) syn ^= s.vec[1 + fi][3];
+            if (fj >= 0) syn ^= s.vec[1 + fj][3];
+            pass = (syn == 0);
+        }
+        uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+        while (ballot) {
+            const int src = __ffs(ballot) - 1;
+            ballot &= ballot - 1;
+            const int sfi = __shfl_sync(0xffffffffu, fi, src), sfj = __shfl_sync(0xffffffffu, fj, src);
+            uint32_t w[3];
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                w[x] = s.vec[0][x];
+                if (sfi >= 0) w[x] ^= s.vec[1 + sfi][x];
+                if (sfj >= 0) w[x] ^= s.vec[1 + sfj][x];
+            }
+            if ((w[0] | w[1] | (w[2] & 0x1FFFu)) != 0 && payload_valid(w)) {
+                bits[0] = w[0]; bits[1] = w[1]; bits[2] = w[2];
+                return base + src + 1;
+            }
+        }
+    }
+    bits[0] = s.vec[0][0]; bits[1] = s.vec[0][1]; bits[2] = s.vec[0][2];
+    return 0;
+}
+
+}  // namespace ft8

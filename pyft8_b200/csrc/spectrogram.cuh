@@ -1,0 +1,88 @@
+// spectrogram.cuh -- S1: waterfall rows for a batch of cycles.
+//
+// Restates AudioIn.get_hop_spectrum (receiver.py:288-293) driven once per 480-sample hop
+// (receiver.py:295-306) for an isolated cycle:
+//     grid[h, k] = 20*log10(|rfft(x[480h-3840 : 480h] * hanning(3840))[k]| + 1e-12),  k < 976, 1 <= h <= 375
+// with x = 0 before the cycle start and grid[0, :] = 1.0 (the reference's initial fill).
+//
+// One group of 128 threads per row, SP_ROWS rows per CTA.  The 3840-point real transform is a
+// 1920-point complex Stockham FFT of z[n] = x[2n] + i*x[2n+1] in shared memory (passes 3,5,8,16);
+// the first pass reads the windowed audio straight from global memory (int16 -> fp32 fused), the
+// epilogue untangles only the 976 bins that are kept and writes dB.  Rows of one CTA are adjacent,
+// so their 7/8-overlapping windows hit L1/L2: HBM sees the audio once and the grid once.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fft.cuh"
+
+namespace ft8 {
+
+constexpr int SP_ROWS = 4;          // rows per CTA
+constexpr int SP_NT = 128;          // threads per row
+constexpr int GRID_ROWS = 376, GRID_COLS = 976, CYCLE_SAMPLES = 180000, NFFT_S = 3840, HOP = 480;
+
+__device__ __forceinline__ float load_sample(const int16_t* a, int i) { return (float)a[i]; }
+__device__ __forceinline__ float load_sample(const float* a, int i) { return a[i]; }
+
+template <typename T>
+__global__ void __launch_bounds__(SP_ROWS* SP_NT)
+k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float* __restrict__ hann,
+              const float2* __restrict__ W1920, const float2* __restrict__ W3840) {
+    extern __shared__ float2 sp_smem[];
+    const int cyc = blockIdx.y;
+    const int g = threadIdx.x / SP_NT, lt = threadIdx.x % SP_NT;
+    const int h = 1 + blockIdx.x * SP_ROWS + g;
+    const bool live = h <= 375;
+    float2* buf = sp_smem + g * 1920;
+    const T* x = audio + (size_t)cyc * CYCLE_SAMPLES;
+    float* out = grid + (size_t)cyc * GRID_ROWS * GRID_COLS;
+    if (blockIdx.x == 0) {
+        for (int k = threadIdx.x; k < GRID_COLS; k += blockDim.x) out[k] = 1.0f;
+    }
+    const int s0 = HOP * h - NFFT_S;      // first sample of the window (may be negative)
+
+    // pass (R=3, S=1) with operands gathered from global memory: z[n] for n = p + 640*j
+    {
+        constexpr int NBF = 640, PER = NBF / SP_NT;
+        float2 a[PER][3];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int p = lt + i * SP_NT;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int n = p + 640 * j;
+                const int si = s0 + 2 * n;
+                float re = 0.f, im = 0.f;
+                if (live && si >= 0) {
+                    const float2 w = *reinterpret_cast<const float2*>(hann + 2 * n);
+                    re = load_sample(x, si) * w.x;
+                    im = load_sample(x, si + 1) * w.y;
+                }
+                a[i][j] = make_float2(re, im);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) Pass<1920, 3, 1>::template compute_store<false>(buf, lt + i * SP_NT, a[i], W1920);
+        __syncthreads();
+    }
+    pass_inplace<1920, 5, 3, SP_NT, false>(buf, lt, W1920, CtaSync());
+    pass_inplace<1920, 8, 15, SP_NT, false>(buf, lt, W1920, CtaSync());
+    pass_inplace<1920, 16, 120, SP_NT, false>(buf, lt, W1920, CtaSync());
+
+    // untangle the real transform for bins 0..975 and write dB
+    if (live) {
+        float* row = out + (size_t)h * GRID_COLS;
+        for (int k = lt; k < GRID_COLS; k += SP_NT) {
+            const float2 zk = buf[k];
+            const float2 zm = buf[k == 0 ? 0 : 1920 - k];
+            const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+            const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));   // -i/2 * (zk - conj(zm))
+            const float2 w = __ldg(&W3840[k]);
+            const float2 X = cadd(e, cmul(o, w));
+            const float mag = sqrtf(fmaf(X.x, X.x, X.y * X.y));
+            row[k] = 20.0f * log10f(mag + 1e-12f);
+        }
+    }
+}
+
+}  // namespace ft8
