@@ -123,6 +123,10 @@ int  ft8_last_kernel_ms(ft8_handle* h, int which, float* ms);
 /* S1  AudioIn.get_hop_spectrum x375 (receiver.py:288-293): audio[B][180000] -> grid_db[B][376][976] float32 dB. */
 int ft8_spectrogram(ft8_handle* h, const void* audio, int audio_dtype, int B, float* grid_db, int mem);
 
+/* S1, live form: exactly AudioIn.get_hop_spectrum (receiver.py:288-293) -- audio_buffer[180000] is the receiver's ring
+ *     buffer (receiver.py:248, 296-299); row_db[976] = 20*log10(|rfft(audio_buffer[-3840:] * hanning)[:976]| + 1e-12). */
+int ft8_hop_spectrum(ft8_handle* h, const void* audio_buffer, int audio_dtype, float* row_db, int mem);
+
 /* S2  Receiver.search (receiver.py:338-367): grid_db[B][grid_rows][976] (grid_rows 376: rows beyond read as 1.0,
  *     or 750: the live ring) -> per cycle up to max_cands candidates sorted by score descending.
  *     cand_f0/cand_h0: int16 [B][max_cands]; cand_score: float [B][max_cands]; n_cand: int32 [B];

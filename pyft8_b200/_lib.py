@@ -60,6 +60,7 @@ SIGNATURES = {
     "ft8_stream": (_P, [_P]),
     "ft8_last_kernel_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
     "ft8_spectrogram": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int]),
+    "ft8_hop_spectrum": (C.c_int, [_P, _P, C.c_int, _P, C.c_int]),
     "ft8_sync": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int]),
     "ft8_llr": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int]),
     "ft8_cycle_spectrum": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int]),

@@ -334,13 +334,16 @@ static CandState cand_state(ft8_handle* h) {
     return cs;
 }
 
-static int launch_spectrogram(ft8_handle* h, const void* d_audio, int dtype, int B, float* d_grid) {
-    dim3 grid((375 + SP_ROWS - 1) / SP_ROWS, B);
+static int launch_spectrogram(ft8_handle* h, const void* d_audio, int dtype, int B, float* d_grid, int row_lo = 1,
+                              int row_hi = 375, int out_rows = GRID_ROWS, int out_row0 = 0, int fill_row0 = 1) {
+    dim3 grid((row_hi - row_lo + SP_ROWS) / SP_ROWS, B);
     const int smem = SP_ROWS * 1920 * (int)sizeof(float2);
     if (dtype == FT8_AUDIO_I16)
-        k_spectrogram<int16_t><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const int16_t*)d_audio, d_grid, h->d_hann, h->d_W1920, h->d_W3840);
+        k_spectrogram<int16_t><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const int16_t*)d_audio, d_grid, h->d_hann, h->d_W1920,
+                                                                          h->d_W3840, row_lo, row_hi, out_rows, out_row0, fill_row0);
     else
-        k_spectrogram<float><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const float*)d_audio, d_grid, h->d_hann, h->d_W1920, h->d_W3840);
+        k_spectrogram<float><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const float*)d_audio, d_grid, h->d_hann, h->d_W1920,
+                                                                        h->d_W3840, row_lo, row_hi, out_rows, out_row0, fill_row0);
     CK(cudaGetLastError());
     return FT8_OK;
 }
@@ -414,6 +417,20 @@ extern "C" int ft8_spectrogram(ft8_handle* h, const void* audio, int audio_dtype
     if (mem == FT8_MEM_HOST) TRY(from_device(h, grid_db, dg, (size_t)B * GRID_ROWS * GRID_COLS * sizeof(float), mem));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventElapsedTime(&h->last_ms[1], h->ev[0], h->ev[1]));
+    return FT8_OK;
+}
+
+extern "C" int ft8_hop_spectrum(ft8_handle* h, const void* audio_buffer, int audio_dtype, float* row_db, int mem) {
+    ENTER(h);
+    if (!audio_buffer || !row_db) return fail(h, FT8_E_BADARG, "ft8_hop_spectrum: bad argument");
+    const void* da;
+    TRY(stage_audio(h, audio_buffer, audio_dtype, 1, mem, &da));
+    float* dr = row_db;
+    if (mem == FT8_MEM_HOST) { TRY(ensure_arena(h, GRID_COLS * sizeof(float))); dr = (float*)h->arena; }
+    // the window over the last 3840 samples of a 180000-sample buffer is row 375 of that buffer's waterfall
+    TRY(launch_spectrogram(h, da, audio_dtype, 1, dr, 375, 375, 1, 375, 0));
+    if (mem == FT8_MEM_HOST) TRY(from_device(h, row_db, dr, GRID_COLS * sizeof(float), mem));
+    CK(cudaStreamSynchronize(h->stream));
     return FT8_OK;
 }
 

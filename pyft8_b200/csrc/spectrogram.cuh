@@ -27,16 +27,17 @@ __device__ __forceinline__ float load_sample(const float* a, int i) { return a[i
 template <typename T>
 __global__ void __launch_bounds__(SP_ROWS* SP_NT)
 k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float* __restrict__ hann,
-              const float2* __restrict__ W1920, const float2* __restrict__ W3840) {
+              const float2* __restrict__ W1920, const float2* __restrict__ W3840, int row_lo, int row_hi, int out_rows,
+              int out_row0, int fill_row0) {
     extern __shared__ float2 sp_smem[];
     const int cyc = blockIdx.y;
     const int g = threadIdx.x / SP_NT, lt = threadIdx.x % SP_NT;
-    const int h = 1 + blockIdx.x * SP_ROWS + g;
-    const bool live = h <= 375;
+    const int h = row_lo + blockIdx.x * SP_ROWS + g;      // grid row = window ending at sample 480*h
+    const bool live = h <= row_hi;
     float2* buf = sp_smem + g * 1920;
     const T* x = audio + (size_t)cyc * CYCLE_SAMPLES;
-    float* out = grid + (size_t)cyc * GRID_ROWS * GRID_COLS;
-    if (blockIdx.x == 0) {
+    float* out = grid + (size_t)cyc * out_rows * GRID_COLS;
+    if (blockIdx.x == 0 && fill_row0) {
         for (int k = threadIdx.x; k < GRID_COLS; k += blockDim.x) out[k] = 1.0f;
     }
     const int s0 = HOP * h - NFFT_S;      // first sample of the window (may be negative)
@@ -71,7 +72,7 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
 
     // untangle the real transform for bins 0..975 and write dB
     if (live) {
-        float* row = out + (size_t)h * GRID_COLS;
+        float* row = out + (size_t)(h - out_row0) * GRID_COLS;
         for (int k = lt; k < GRID_COLS; k += SP_NT) {
             const float2 zk = buf[k];
             const float2 zm = buf[k == 0 ? 0 : 1920 - k];

@@ -85,6 +85,13 @@ class Engine:
         self._check(self._lib.ft8_spectrogram(self._h, _ptr(a), dt, a.shape[0], _ptr(out), L.MEM_HOST))
         return out
 
+    def hop_spectrum(self, audio_buffer):
+        """AudioIn.get_hop_spectrum: dB row of the window over the last 3840 samples of the 180000-sample ring buffer."""
+        a, dt = self._audio(audio_buffer)
+        out = np.empty(L.GRID_COLS, np.float32)
+        self._check(self._lib.ft8_hop_spectrum(self._h, _ptr(a), dt, _ptr(out), L.MEM_HOST))
+        return out
+
     # ---- S2
     def sync(self, grid, odd_even=0, want_payload=True):
         g = np.ascontiguousarray(grid, np.float32)

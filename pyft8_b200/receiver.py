@@ -1,0 +1,384 @@
+"""Drop-in for the receive side of PyFT8/receiver.py, running on the CUDA library.
+
+Mirrors the reference's call surface:
+  AudioIn      ring buffer + live waterfall (`search_grid` stays a live numpy array the GUI can view),
+               `_callback(in_data, ...)`, `get_hop_spectrum(ptr)`, `get_cycle_spectrum()`      receiver.py:225-306
+  Candidate    same constructor, attributes and one-pass-per-call `decode()` / `check_and_package()`  receiver.py:29-222
+  Receiver     same constructor keywords, `search()`, `set_band()`, `manage_cycle()`            receiver.py:310-412
+plus the batched entry point this package adds: `Receiver.decode_cycles(audio[B,180000])` / module-level
+`decode_cycles(...)`, which runs the whole pass schedule on the device (ft8_decode_cycles).
+
+What differs, on purpose: no PyAudio device handling (the caller feeds `_callback`), threads are only started on
+request, and the clock is injectable.  All DSP/FEC arithmetic goes through the C ABI; there is no numpy fallback.
+"""
+import threading
+
+import numpy as np
+
+from . import _lib as L
+from .engine import Engine, bits91_to_int
+from .messages import unpack
+from .time_utils import TimeUtils
+from . import decoders
+
+WATERFALL_DOWNSAMPLE = 2
+T_CYC = 15
+N_SYMS = 79
+SYM_RATE = 6.25
+SAMP_RATE = 12000
+COSTAS = [3, 1, 4, 0, 6, 5, 2]
+PAYLOAD_SYMB_IDXS = list(range(7, 36)) + list(range(43, 72))
+COSTAS_SYMB_IDXS = list(range(7)) + list(range(36, 43)) + list(range(72, 79))
+
+ap_patterns = [
+    ['NoAP', 0, []],
+    ['CQ', 0, [0] * 26 + [1, 0, 0]],
+    ['RR73', 58, [0, 1, 1, 1, 1, 1, 1, 0, 0, 1, 1, 1, 0, 1, 0, 1, 0, 0, 1]],
+    ['73', 58, [0, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, 1, 0, 1, 0, 0, 0, 0, 1]],
+    ['RRR', 58, [0, 1, 1, 1, 1, 1, 1, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 0, 1]],
+]
+
+
+class Candidate:
+    """One sync candidate and its pass state machine (receiver.py:29-222), each step executed by the CUDA library."""
+
+    def __init__(self, origin, search_grid_bounds, payload_on_search_grid, get_cycle_spectrum, on_message, llr_sd_min=5,
+                 engine=None, time_utils=None):
+        self.origin = origin
+        self.search_grid_bounds = search_grid_bounds
+        self.payload_on_search_grid = payload_on_search_grid
+        self.get_cycle_spectrum = get_cycle_spectrum
+        self.on_message = on_message
+        self.llr_sd = 0
+        self.llr_sd_min = llr_sd_min
+        self.ipass = 0
+        self.signal_grid = None
+        self.source = None
+        self.tweaks = f"t:{0:+03d} f:{0:+03d}"
+        self.saved_llrs = []
+        self.decode_result = None
+        self.n_sync_matches = 100
+        self.serial_id = None
+        self.decode_notes = ''
+        self._engine = engine
+        self._tu = time_utils or TimeUtils()
+
+    def _eng(self):
+        return self._engine or decoders.get_engine()
+
+    def check_and_package(self, duplicate_filter):
+        self.msg_text = ' '.join(self.decode_result)
+        key = self.origin['cyclestart_string'] + self.msg_text
+        if key not in duplicate_filter:
+            duplicate_filter.add(key)
+            o = self.origin
+            their_snr = f"{self.snr:+03d}"
+            tsec, fHz = o['tsec'], o['fHz']
+            self.on_message({
+                "band": o['band'], "tsec": tsec, "fHz": fHz, "msg_tuple": self.decode_result, "their_snr": their_snr,
+                "their_tx_cycle": o['odd_even'],
+                "all_txt_format": f"{o['cyclestart_string']} {their_snr} {(tsec - 0.6):4.1f} {fHz:4.0f} ~ {self.msg_text}",
+                'cyclestart_string': o['cyclestart_string'], "decode_completed": self._tu.time(), 'tweaks': self.tweaks,
+                'decode_notes': self.decode_notes + self.tweaks})
+        self.decode_result = 'stop'
+
+    def decode(self, current_max_ipass):
+        if (self.ipass <= current_max_ipass) and (self.decode_result != 'stop'):
+            if self.ipass == 0:
+                self._get_llr_grid()
+                self.llr0 = self.llr.copy()
+                for ap in ap_patterns:
+                    self._set_AP(ap)
+                    self._decode_good91()
+                    self._decode_ldpc(35, 5, False)
+            if self.ipass == 1:
+                self._get_llr_fine()
+            if self.ipass == 2:
+                self.llr0 = self.llr.copy()
+                for ap in ap_patterns[:2]:
+                    self._set_AP(ap)
+                    self._decode_good91()
+            if self.ipass == 3:
+                for ap in ap_patterns[:2]:
+                    self._set_AP(ap)
+                    self._decode_ldpc(35, 5, False)
+            if self.ipass == 4:
+                for ap in ap_patterns:
+                    self._set_AP(ap)
+                    self._decode_ldpc(90, 20, True)
+            if self.ipass == 5:
+                for ap in ap_patterns:
+                    self._set_AP(ap)
+                    self._decode_osd()
+            if self.ipass == 6:
+                for pat_llr in self.saved_llrs:
+                    self.pat_name, self.llr = pat_llr
+                    self._decode_osd()
+            if self.ipass == 7:
+                self.decode_result = 'stop'
+            self.ipass += 1
+
+    def _set_AP(self, ap_pattern):
+        self.pat_name, b0, bit_pattern = ap_pattern
+        self.llr = self.llr0.copy()
+        for b, bval in enumerate(bit_pattern):
+            self.llr[b0 + b] = (bval * 2 - 1) * 5
+        if self.pat_name == 'CQ':
+            self.llr[74:76] = -5
+            self.llr[76] = 5
+            self.llr[57:59] = -5
+
+    def _decode_good91(self):
+        if not self.decode_result:
+            self.decode_notes = f'{self.source}_{self.pat_name}_GOOD91 '
+            self.decode_result = decoders.crc_unpack91(self.llr[:91])
+
+    def _decode_ldpc(self, max_nc0, max_its, save_llr):
+        if not self.decode_result:
+            self.decode_notes = f'{self.source}_{self.pat_name}_LDPC{max_its}'
+            self.decode_result, self.n_its, output_llr = decoders.ldpc_decode(self.llr, max_nc0, max_its)
+            if save_llr and not self.decode_result and len(output_llr) == 174:
+                self.saved_llrs.append((f"{self.pat_name}_LDPC{max_its}", output_llr))
+
+    def _decode_osd(self):
+        if not self.decode_result:
+            self.decode_notes = f'{self.source}_{self.pat_name}_OSD'
+            self.decode_result = decoders.osd_012(self.llr)
+
+    def _get_llr_grid(self):
+        self._dB_to_llr(self.payload_on_search_grid)
+        self.source = 'grid'
+
+    def _get_llr_fine(self):
+        self.source = 'fine'
+        spec = self.get_cycle_spectrum()
+        o = self.origin
+        r = self._eng().fine(spec, [0], [o['f0_idx']], [o['h0_idx']])
+        ttweak, ftweak = int(r['tt'][0]), int(r['ff'][0])
+        self.signal_grid = r['grid'][0]
+        self.tweaks = f" t:{ttweak:+03d} f:{ftweak:+03d}"
+        self.n_sync_matches = int(r['nsync'][0])
+        if self.n_sync_matches > 6:
+            o.update({'tsec': float(o['tsec'] + ttweak / 200), 'fHz': float(o['fHz'] + ftweak / 16)})
+            self.snr = int(r['snr'][0])
+            self.llr_sd = float(r['sd'][0])
+            self.llr = r['llr'][0].copy()
+            if self.llr_sd <= self.llr_sd_min:
+                self.decode_result = 'stop'
+        else:
+            self.decode_result = 'stop'
+
+    def _dB_to_llr(self, payload_dB_grid):
+        if payload_dB_grid is None:
+            return
+        llr, sd, snr = self._eng().llr(payload_dB_grid)
+        self.snr = int(snr[0])
+        self.llr_sd = float(sd[0])
+        self.llr = llr[0].copy()
+        if self.llr_sd <= self.llr_sd_min:
+            self.decode_result = 'stop'
+
+
+class AudioIn:
+    """Ring buffer + live waterfall (receiver.py:225-306) without the PyAudio plumbing: feed `_callback` yourself."""
+
+    def __init__(self, search_freq_range, input_device_keywords=None, engine=None, time_utils=None):
+        self._engine = engine
+        self._tu = time_utils or TimeUtils()
+        self.input_device_idx = None
+        self.search_hps, self.search_bpt = 4, 2
+        self.search_freq_range = search_freq_range
+        self.search_fft_len = int(self.search_bpt * SAMP_RATE // SYM_RATE)
+        self.samples_perhop = int(SAMP_RATE / (SYM_RATE * self.search_hps))
+        self.df = SYM_RATE / self.search_bpt
+        self.search_f0_idx_range = [int(search_freq_range[0] / self.df), int(search_freq_range[1] / self.df)]
+        self.search_hops_per_cycle = int(T_CYC * SYM_RATE * self.search_hps)
+        self.search_hops_per_grid = 2 * self.search_hops_per_cycle
+        self.dt = T_CYC / self.search_hops_per_cycle
+        self.search_grid = np.ones((self.search_hops_per_grid, self.search_f0_idx_range[1] + 8 * self.search_bpt), np.float32)
+        if self.search_grid.shape[1] != L.GRID_COLS:
+            raise ValueError("the CUDA path is built for search_freq_range[1] = 3000 Hz (976 grid columns)")
+        self.samples_per_cycle = int(SAMP_RATE * T_CYC)
+        self.search_grid_ptr = int(self._tu.grid_time() * self.search_hops_per_grid / (2 * T_CYC))
+        self.last_get_cycle_spectrum = 0
+        self.last_get_hop_spectrum = 0
+        self.waterfall_data = self._set_waterfall_data()
+        self.audio_buffer = np.zeros(self.samples_per_cycle, np.float32)
+        self.fft1_buffer = np.zeros(192000, np.float32)
+
+    def _eng(self):
+        return self._engine or decoders.get_engine()
+
+    def _set_waterfall_data(self):
+        d = WATERFALL_DOWNSAMPLE
+        return {'data': self.search_grid[::d, ::d].T, 'df': self.df * d, 'dt': self.dt * d,
+                'sig_w': int(79 * self.search_hps / d), 'sig_h': int(8 * self.search_bpt / d),
+                'pixels_per_cycle': int(self.search_hops_per_cycle / d)}
+
+    def get_cycle_spectrum(self):
+        if self.search_grid_ptr != self.last_get_cycle_spectrum:
+            samps_offset = int((T_CYC - self._tu.cycle_time()) * SAMP_RATE)
+            aligned = np.roll(self.audio_buffer[-self.samples_per_cycle:], -samps_offset)
+            self.cycle_spectrum = self._eng().cycle_spectrum(aligned)[0]
+            self.last_get_cycle_spectrum = self.search_grid_ptr
+        return self.cycle_spectrum
+
+    def get_hop_spectrum(self, grid_ptr):
+        if grid_ptr != self.last_get_hop_spectrum:
+            self.search_grid[grid_ptr, :] = self._eng().hop_spectrum(self.audio_buffer)
+            self.last_get_hop_spectrum = grid_ptr
+
+    def _callback(self, in_data, frame_count=None, time_info=None, status_flags=None):
+        samples = np.frombuffer(in_data, dtype=np.int16)
+        n = len(samples)
+        self.audio_buffer[:-n] = self.audio_buffer[n:]
+        self.audio_buffer[-n:] = samples
+        self.search_grid_ptr = (self.search_grid_ptr + 1) % self.search_hops_per_grid
+        if self.search_grid_ptr == 0:
+            tg = self._tu.grid_time()
+            if tg > 0.1:
+                self.search_grid_ptr = int(tg * self.search_hops_per_grid / (2 * T_CYC))
+        self.get_hop_spectrum(self.search_grid_ptr)
+        return (None, 0)
+
+
+def record_to_message(r, cyclestart_string="", band=None, odd_even=0, now=0.0):
+    """ft8_record -> the dict Candidate.check_and_package emits (receiver.py:61-64), or None if unpack rejects."""
+    msg = unpack(bits91_to_int(r["bits91"]) >> 14)
+    if msg is None:
+        return None
+    src = "grid" if r["ipass"] == 0 else "fine"
+    tweaks = "t:+00 f:+00" if r["ipass"] < 2 else " t:%+03d f:%+03d" % (r["ttweak"], r["ftweak"])
+    notes = f"{src}_{L.AP_NAMES[r['ap']]}_{L.METHOD_NAMES[r['method']]}"
+    # python-float origin arithmetic of the reference (receiver.py:168-169, 350-351)
+    tsec, fHz = r["h0_idx"] / 25.0, 3.125 * float(r["f0_idx"])
+    if r["ipass"] >= 2:
+        tsec, fHz = float(tsec + int(r["ttweak"]) / 200), float(fHz + int(r["ftweak"]) / 16)
+    snr = f"{int(r['snr']):+03d}"
+    text = " ".join(msg)
+    return {"band": band, "tsec": tsec, "fHz": fHz, "msg_tuple": msg, "their_snr": snr, "their_tx_cycle": odd_even,
+            "all_txt_format": f"{cyclestart_string} {snr} {(tsec - 0.6):4.1f} {fHz:4.0f} ~ {text}",
+            "cyclestart_string": cyclestart_string, "decode_completed": now, "tweaks": tweaks,
+            "decode_notes": notes + tweaks, "bits77": bits91_to_int(r["bits91"]) >> 14, "cycle": int(r["cycle"])}
+
+
+class Receiver:
+    def __init__(self, input_device_keywords, on_message, sync_score_min=85, max_cands=200, search_freq_range=[100, 3000],
+                 search_time_range=[-2.5 + 0.5, 2.5 + 0.5], verbose=False, engine=None, clock=None, start_thread=False,
+                 batch_cycles=1, device=0):
+        if list(search_time_range) != [-2.0, 3.0] or list(search_freq_range) != [100, 3000]:
+            raise ValueError("the CUDA path is built for the reference's default search ranges ([100,3000] Hz, [-2,3] s)")
+        self._tu = TimeUtils(clock)
+        # sync engine returns every thresholded bin (max_cands=928) so that search() can honour any f-index subset
+        self.engine = engine or Engine(device=device, max_cycles=max(1, batch_cycles), max_cands=928,
+                                       sync_score_min=sync_score_min)
+        decoders.set_engine(self.engine)
+        self._batch_engine = None
+        self._device = device
+        self.audio_in = AudioIn(search_freq_range, input_device_keywords, self.engine, self._tu)
+        self.on_message = on_message
+        self.sync_score_min, self.max_cands = sync_score_min, max_cands
+        self.candidates = []
+        self.verbose = verbose
+        self.search_h0_range = [int((t + 0.5) * self.audio_in.search_hps * SYM_RATE) for t in search_time_range]
+        self.search_start_hop = self.search_h0_range[1] + 43 * self.audio_in.search_hps
+        self.band = None
+        self.cand_serial = 0
+        self._tu.set_cycle_length(T_CYC)
+        if start_thread:
+            threading.Thread(target=self.manage_cycle, daemon=True).start()
+
+    def search(self, cyclestart_string, odd_even, search_f_idxs):
+        ai = self.audio_in
+        f0, h0, sc, n, pay = self.engine.sync(ai.search_grid, odd_even=odd_even, want_payload=False)
+        wanted = set(search_f_idxs)
+        cycle_h0 = odd_even * ai.search_hops_per_cycle
+        hops_per_sig = ai.search_hps * PAYLOAD_SYMB_IDXS[-1]
+        cands = []
+        for i in range(int(n[0])):
+            if int(f0[0, i]) not in wanted:
+                continue
+            f0_idx, h0_idx = int(f0[0, i]), int(h0[0, i])
+            origin = {'h0_idx': h0_idx, 'f0_idx': f0_idx, 'tsec': h0_idx / (ai.search_hps * SYM_RATE),
+                      'fHz': SYM_RATE * f0_idx / ai.search_bpt, 'score': float(sc[0, i]),
+                      'cyclestart_string': cyclestart_string, 'band': self.band, 'odd_even': odd_even}
+            g0 = cycle_h0 + h0_idx + ai.search_hps
+            hops = np.array([(g0 + ai.search_hps * s) % ai.search_hops_per_grid for s in PAYLOAD_SYMB_IDXS])
+            freqs = np.array([f0_idx + ai.search_bpt // 2 + t * ai.search_bpt for t in range(8)])
+            c = Candidate(origin, [g0, cycle_h0 + h0_idx + hops_per_sig], ai.search_grid[hops, :][:, freqs],
+                          ai.get_cycle_spectrum, self.on_message, engine=self.engine, time_utils=self._tu)
+            self.cand_serial = (self.cand_serial + 1) % 1000
+            c.serial_id = self.cand_serial
+            cands.append(c)
+            if len(cands) >= self.max_cands:
+                break
+        return cands
+
+    def set_band(self, band):
+        self.band = band
+
+    def step(self, duplicate_filter):
+        """One pass of the reference's scheduler body (receiver.py:389-398): returns the number of candidates advanced."""
+        ai = self.audio_in
+        todo = [c for c in self.candidates if (not c.decode_result) and
+                not (c.search_grid_bounds[0] <= ai.search_grid_ptr <= c.search_grid_bounds[1])]
+        todo.sort(key=lambda c: c.llr_sd, reverse=True)
+        for c in todo:
+            c.decode(100)
+            if c.decode_result is not None and c.decode_result != 'stop':
+                c.check_and_package(duplicate_filter)
+        return len(todo)
+
+    def manage_cycle(self):
+        duplicate_filter = set()
+        prev = 0
+        searched = False
+        ai = self.audio_in
+        while True:
+            self._tu.sleep(0.1)
+            pos = ai.search_grid_ptr % ai.search_hops_per_cycle
+            if pos < prev:
+                searched = False
+            prev = pos
+            self.step(duplicate_filter)
+            if not searched and pos > self.search_start_hop:
+                cs = self._tu.cyclestart_string(self._tu.time())
+                self.candidates = self.search(cs, self._tu.odd_even(),
+                                              range(ai.search_f0_idx_range[0], ai.search_f0_idx_range[1]))
+                searched = True
+
+    # ------------------------------------------------------------------ batched entry (ours)
+    def decode_cycles(self, audio, odd_even=0, cyclestart_strings=None, emit=True):
+        """audio [B,180000] int16/float32 -> list (per cycle) of message dicts, in the reference's emission order."""
+        a = np.ascontiguousarray(audio)
+        if a.ndim == 1:
+            a = a[None]
+        B = a.shape[0]
+        if self._batch_engine is None or self._batch_engine.max_cycles < B:
+            if self._batch_engine is not None:
+                self._batch_engine.close()
+            self._batch_engine = Engine(device=self._device, max_cycles=B, max_cands=self.max_cands,
+                                        sync_score_min=self.sync_score_min)
+        rec, n = self._batch_engine.decode_cycles(a, odd_even)
+        out = [[] for _ in range(B)]
+        seen = [set() for _ in range(B)]
+        for r in rec:
+            cyc = int(r["cycle"])
+            cs = cyclestart_strings[cyc] if cyclestart_strings else ""
+            m = record_to_message(r, cs, self.band, odd_even, self._tu.time())
+            if m is None:
+                continue
+            key = cs + " ".join(m["msg_tuple"])          # de-dup on text like receiver.py:53
+            if key in seen[cyc]:
+                continue
+            seen[cyc].add(key)
+            out[cyc].append(m)
+            if emit and self.on_message:
+                self.on_message(m)
+        return out
+
+
+def decode_cycles(audio, odd_even=0, device=0, **kw):
+    """Convenience: decode a batch of isolated cycles with default receiver settings."""
+    rx = Receiver("", None, device=device, **kw)
+    return rx.decode_cycles(audio, odd_even, emit=False)

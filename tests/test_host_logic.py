@@ -1,0 +1,118 @@
+"""CPU tests of the host-side Python that surrounds the CUDA path (message text, records, sharding, generator)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from conftest import ROOT, load_golden
+from pyft8_b200 import messages, synth
+from pyft8_b200.engine import bits91_to_int, int_to_bits91
+from pyft8_b200.sharding import gather_records, shard_range
+from pyft8_b200 import _lib as L
+
+
+def test_unpack_matches_reference_on_random_payloads():
+    c = load_golden("codec.npz")
+    for h, acc, txt in zip(c["payload_hex"], c["accepted"], c["text"]):
+        messages.call_hashes.clear()
+        r = messages.unpack(int(h, 16))
+        assert (r is not None) == bool(acc), h
+        if acc:
+            assert "|".join(r) == txt
+
+
+def test_hash_history_resolves_brackets():
+    messages.call_hashes.clear()
+    messages.add_call_hashes("G1OJS")
+    h22 = messages.hashes_for_calls["G1OJS"][2][0]
+    payload = ((2063592 + h22) << 49) | (synth.pack_call28("EA6VQ")[0] << 20) | (32403 << 3) | 1
+    assert messages.unpack(payload) == ("<G1OJS>", "EA6VQ", "RR73")
+    messages.call_hashes.clear()
+    assert messages.unpack(payload) == ("<...>", "EA6VQ", "RR73")
+
+
+def test_bits91_roundtrip():
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        v = int.from_bytes(rng.bytes(12), "big") >> 5
+        assert bits91_to_int(int_to_bits91(v)) == v
+
+
+def test_pack_encode_roundtrip_through_unpack():
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        m = synth.random_message(rng)
+        b = synth.pack77(*m)
+        assert messages.unpack(b) == m
+        cw = synth.codeword_bits(b)
+        assert len(cw) == 174
+        # every parity check of the decoder graph is satisfied by the encoder's codeword
+        from pyft8_b200.tables import CHECK_VARS
+        for row in CHECK_VARS:
+            assert sum(cw[v] for v in row if v >= 0) % 2 == 0
+
+
+def test_record_to_message_format():
+    from pyft8_b200.receiver import record_to_message
+    b77 = synth.pack77("CQ", "G1OJS", "IO90")
+    r = np.zeros(1, L.RECORD_DTYPE)[0]
+    r["bits91"] = int_to_bits91((b77 << 14) | synth.crc14(b77))
+    r["f0_idx"], r["h0_idx"], r["snr"], r["ipass"], r["ap"], r["method"], r["ttweak"], r["ftweak"] = 400, 15, -7, 4, 1, 2, -6, -32
+    m = record_to_message(r, "240101_000000")
+    assert m["msg_tuple"] == ("CQ", "G1OJS", "IO90")
+    assert m["decode_notes"] == "fine_CQ_LDPC20 t:-06 f:-32"
+    assert m["their_snr"] == "-07"
+    assert abs(m["tsec"] - (15 / 25 - 0.03)) < 1e-12 and abs(m["fHz"] - 1248.0) < 1e-12
+    assert m["all_txt_format"] == "240101_000000 -07 -0.0 1248 ~ CQ G1OJS IO90"
+    r["ipass"], r["method"], r["ap"] = 0, 0, 0
+    assert record_to_message(r)["decode_notes"] == "grid_NoAP_GOOD91 t:+00 f:+00"
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 8, 100000):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch.distributed as dist
+from pyft8_b200 import _lib as L
+from pyft8_b200.sharding import shard_range, gather_records
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+lo, hi = shard_range(5, dist.get_rank(), 2)
+rec = np.zeros(2 * (hi - lo), L.RECORD_DTYPE)
+rec["cycle"] = np.repeat(np.arange(hi - lo), 2)
+rec["cand"] = 10 * dist.get_rank() + np.arange(len(rec))
+out = gather_records(rec, lo, dist)
+if dist.get_rank() == 0:
+    assert list(out["cycle"]) == [0, 0, 1, 1, 2, 2, 3, 3, 4, 4], list(out["cycle"])
+    assert list(out["cand"][:6]) == [0, 1, 2, 3, 4, 5] and list(out["cand"][6:]) == [10, 11, 12, 13]
+    print("GATHER_OK")
+else:
+    assert out is None
+dist.destroy_process_group()
+'''
+
+
+def test_gather_records_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHER_OK" in outs[0]
+
+
+def test_gather_records_single_process():
+    rec = np.zeros(3, L.RECORD_DTYPE)
+    out = gather_records(rec, 7)
+    assert list(out["cycle"]) == [7, 7, 7] and list(rec["cycle"]) == [0, 0, 0]
