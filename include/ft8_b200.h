@@ -116,8 +116,10 @@ int  ft8_get_stats(ft8_handle* h, ft8_stats* out);
 int  ft8_synchronize(ft8_handle* h);
 /* CUDA stream of the handle (cudaStream_t as void*), for callers that enqueue their own work / events on it. */
 void* ft8_stream(ft8_handle* h);
-/* Milliseconds spent on the device by the kernels of the last call of the given kind (CUDA events on the
- * handle's stream): which = 0 whole ft8_decode_cycles device section, 1 spectrogram kernel, 2 sync kernels. */
+/* Milliseconds spent on the device (CUDA events on the handle's stream).  After ft8_decode_cycles: which = 0 whole
+ * device section, 1 spectrogram, 2 sync (scores + top-K), 3 cycle spectrum, 4 pass 0 (grid LLR + GOOD91 + LDPC5),
+ * 5 fine sync, 6 passes 2-4 (LDPC), 7 passes 5-6 (OSD), 8 record collection.  After a stand-alone ft8_spectrogram /
+ * ft8_sync call: 1 / 2 = that kernel.  After ft8_ldpc / ft8_osd: 0 = that kernel. */
 int  ft8_last_kernel_ms(ft8_handle* h, int which, float* ms);
 
 /* S1  AudioIn.get_hop_spectrum x375 (receiver.py:288-293): audio[B][180000] -> grid_db[B][376][976] float32 dB. */

@@ -60,8 +60,8 @@ struct ft8_handle {
     DevStats* h_stats = nullptr;      // pinned
     // generic arena for the stand-alone stage ops
     void* arena = nullptr; size_t arena_bytes = 0;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    float last_ms[3] = {0, 0, 0};
+    cudaEvent_t ev[12] = {};          // ev[0..8]: stage boundaries of ft8_decode_cycles; ev[10], ev[11]: stand-alone ops
+    float last_ms[9] = {};            // see ft8_last_kernel_ms
     ft8_stats stats{};
 };
 
@@ -318,7 +318,7 @@ extern "C" int ft8_get_stats(ft8_handle* h, ft8_stats* out) {
     return FT8_OK;
 }
 extern "C" int ft8_last_kernel_ms(ft8_handle* h, int which, float* ms) {
-    if (!h || !ms || which < 0 || which > 2) return FT8_E_BADARG;
+    if (!h || !ms || which < 0 || which > 8) return FT8_E_BADARG;
     *ms = h->last_ms[which];
     return FT8_OK;
 }
@@ -411,12 +411,12 @@ extern "C" int ft8_spectrogram(ft8_handle* h, const void* audio, int audio_dtype
     const void* da;
     TRY(stage_audio(h, audio, audio_dtype, B, mem, &da));
     float* dg = mem == FT8_MEM_DEVICE ? grid_db : h->d_grid;
-    CK(cudaEventRecord(h->ev[0], h->stream));
+    CK(cudaEventRecord(h->ev[10], h->stream));
     TRY(launch_spectrogram(h, da, audio_dtype, B, dg));
-    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaEventRecord(h->ev[11], h->stream));
     if (mem == FT8_MEM_HOST) TRY(from_device(h, grid_db, dg, (size_t)B * GRID_ROWS * GRID_COLS * sizeof(float), mem));
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaEventElapsedTime(&h->last_ms[1], h->ev[0], h->ev[1]));
+    CK(cudaEventElapsedTime(&h->last_ms[1], h->ev[10], h->ev[11]));
     return FT8_OK;
 }
 
@@ -450,9 +450,9 @@ extern "C" int ft8_sync(ft8_handle* h, const float* grid_db, int grid_rows, int 
     CK(cudaMemsetAsync(h->d_f0, 0, N * 2, h->stream));
     CK(cudaMemsetAsync(h->d_h0, 0, N * 2, h->stream));
     CK(cudaMemsetAsync(h->d_score, 0, N * 4, h->stream));
-    CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(cudaEventRecord(h->ev[10], h->stream));
     TRY(launch_sync(h, dg, grid_rows, B, odd_even));
-    CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(cudaEventRecord(h->ev[11], h->stream));
     float* d_pay = nullptr;
     if (payload_db) {
         if (mem == FT8_MEM_DEVICE) d_pay = payload_db;
@@ -475,7 +475,7 @@ extern "C" int ft8_sync(ft8_handle* h, const float* grid_db, int grid_rows, int 
     TRY(from_device(h, n_cand, h->d_ncand, (size_t)B * 4, mem));
     if (payload_db && mem == FT8_MEM_HOST) TRY(from_device(h, payload_db, d_pay, N * 58 * 8 * sizeof(float), mem));
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaEventElapsedTime(&h->last_ms[2], h->ev[2], h->ev[3]));
+    CK(cudaEventElapsedTime(&h->last_ms[2], h->ev[10], h->ev[11]));
     return FT8_OK;
 }
 
@@ -568,11 +568,11 @@ extern "C" int ft8_ldpc(ft8_handle* h, float* llr, int N, int max_ncheck0, int m
         dl = c.take<float>((size_t)N * 174); dst = c.take<int32_t>(N); dn = c.take<int32_t>(N); db = c.take<uint32_t>((size_t)N * 3);
         TRY(to_device(h, dl, llr, (size_t)N * 174 * 4, mem));
     }
-    CK(cudaEventRecord(h->ev[4], h->stream));
+    CK(cudaEventRecord(h->ev[10], h->stream));
     k_ldpc_batch<<<std::min(persistent_blocks(h, 8), (N + WARPS_PER_CTA - 1) / WARPS_PER_CTA), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
         dl, N, max_ncheck0, max_iters, dst, dn, db);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev[5], h->stream));
+    CK(cudaEventRecord(h->ev[11], h->stream));
     if (mem == FT8_MEM_HOST) {
         TRY(from_device(h, llr, dl, (size_t)N * 174 * 4, mem));
         TRY(from_device(h, status, dst, (size_t)N * 4, mem));
@@ -580,7 +580,7 @@ extern "C" int ft8_ldpc(ft8_handle* h, float* llr, int N, int max_ncheck0, int m
         TRY(from_device(h, bits91, db, (size_t)N * 12, mem));
     }
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[4], h->ev[5]));
+    CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[10], h->ev[11]));
     return FT8_OK;
 }
 
@@ -597,17 +597,17 @@ extern "C" int ft8_osd(ft8_handle* h, const float* llr, int N, int singleflips, 
         TRY(to_device(h, l, llr, (size_t)N * 174 * 4, mem));
         dl = l;
     }
-    CK(cudaEventRecord(h->ev[4], h->stream));
+    CK(cudaEventRecord(h->ev[10], h->stream));
     k_osd_batch<<<std::min(persistent_blocks(h, 8), (N + WARPS_PER_CTA - 1) / WARPS_PER_CTA), WARPS_PER_CTA * 32, sizeof(OsdSmem), h->stream>>>(
         dl, N, singleflips, doubleflips, df, db);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev[5], h->stream));
+    CK(cudaEventRecord(h->ev[11], h->stream));
     if (mem == FT8_MEM_HOST) {
         TRY(from_device(h, found, df, (size_t)N * 4, mem));
         TRY(from_device(h, bits91, db, (size_t)N * 12, mem));
     }
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[4], h->ev[5]));
+    CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[10], h->ev[11]));
     return FT8_OK;
 }
 
@@ -664,42 +664,46 @@ extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dty
     const void* da;
     TRY(stage_audio(h, audio, audio_dtype, B, mem, &da));
     int launches = 0;
-    CK(cudaEventRecord(h->ev[0], h->stream));
     CK(cudaMemsetAsync(h->d_counts, 0, 4 * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), h->stream));
+    CK(cudaEventRecord(h->ev[0], h->stream));
     // S1
-    CK(cudaEventRecord(h->ev[2], h->stream));
     TRY(launch_spectrogram(h, da, audio_dtype, B, h->d_grid)); ++launches;
-    CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(cudaEventRecord(h->ev[1], h->stream));
     // S2
     TRY(launch_sync(h, h->d_grid, GRID_ROWS, B, odd_even)); launches += 2;
-    CK(cudaEventRecord(h->ev[4], h->stream));
-    // F1 (independent of S1/S2; same stream for now)
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    // F1 (independent of S1/S2; same stream)
     TRY(launch_cycle_spectrum(h, da, audio_dtype, B, h->d_spec, FINE_SPEC_STRIDE, FINE_SPEC_STRIDE - 1));
     launches += 2 * ((B + (int)h->y_cycles - 1) / (int)h->y_cycles);
+    CK(cudaEventRecord(h->ev[3], h->stream));
     CandState cs = cand_state(h);
     // ipass 0
     k_pass0<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
         cs, N, h->d_grid, GRID_ROWS, cycle_h0, h->cfg.llr_sd_min, nullptr, 0, h->d_list_fine, h->d_counts + 0, h->d_stats);
     CK(cudaGetLastError()); ++launches;
+    CK(cudaEventRecord(h->ev[4], h->stream));
     // ipass 1
     k_fine<<<persistent_blocks(h, 4), FINE_NT, FINE_SMEM_BYTES, h->stream>>>(
         h->d_spec, FINE_SPEC_STRIDE, h->d_list_fine, h->d_counts + 0, 0, h->d_cycle_of, h->d_f0, h->d_h0, h->d_W3200, h->d_fine,
         h->d_llr_fine, nullptr);
     CK(cudaGetLastError()); ++launches;
+    CK(cudaEventRecord(h->ev[5], h->stream));
     // ipass 2-4
     k_pass234<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
         cs, h->d_list_fine, h->d_counts + 0, h->cfg.llr_sd_min, h->d_list_osd, h->d_counts + 1, h->d_stats);
     CK(cudaGetLastError()); ++launches;
+    CK(cudaEventRecord(h->ev[6], h->stream));
     // ipass 5-6
     k_osd_items<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(OsdSmem), h->stream>>>(
         cs, h->d_list_osd, h->d_counts + 1, h->cfg.osd_singleflips, h->cfg.osd_doubleflips, h->d_stats);
     CK(cudaGetLastError()); ++launches;
     k_osd_resolve<<<persistent_blocks(h, 2), 128, 0, h->stream>>>(cs, h->d_list_osd, h->d_counts + 1, h->d_stats);
     CK(cudaGetLastError()); ++launches;
+    CK(cudaEventRecord(h->ev[7], h->stream));
     k_collect<<<persistent_blocks(h, 4), 256, 0, h->stream>>>(cs, N, h->d_fine, h->d_rec, h->d_counts + 2);
     CK(cudaGetLastError()); ++launches;
-    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaEventRecord(h->ev[8], h->stream));
     CK(cudaMemcpyAsync(h->h_counts, h->d_counts, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -708,9 +712,8 @@ extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dty
         CK(cudaMemcpyAsync(h->h_rec, h->d_rec, (size_t)nrec * sizeof(ft8_record), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
-    CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]));
-    CK(cudaEventElapsedTime(&h->last_ms[1], h->ev[2], h->ev[3]));
-    CK(cudaEventElapsedTime(&h->last_ms[2], h->ev[3], h->ev[4]));
+    CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[8]));
+    for (int i = 1; i <= 8; ++i) CK(cudaEventElapsedTime(&h->last_ms[i], h->ev[i - 1], h->ev[i]));
     // emission order (receiver.py:389-398): pass by pass; inside a pass by llr_sd descending (the fine sd from
     // ipass 2 on, all-equal before), ties by candidate rank; then de-dup on the payload (receiver.py:53-55)
     std::sort(h->h_rec, h->h_rec + nrec, [](const ft8_record& a, const ft8_record& b) {
