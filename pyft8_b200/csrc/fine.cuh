@@ -152,12 +152,12 @@ __device__ __forceinline__ void fine_ifft(float2* buf, const float2* __restrict_
     pass_inplace<3200, 16, 200, FINE_NT, true>(buf, tid, W3200, CtaSync());
 }
 
-// |DFT32(z[i0 : i0+32])[t]| / 3200  (numpy's ifft carries the 1/N)
-__device__ __forceinline__ float tone_mag(const float2* z, int i0, int t) {
+// |DFT32(z[i0 : i0+32])[t]| / 3200  (numpy's ifft carries the 1/N).  w32 = shared copy of exp(-2 pi i m / 32).
+__device__ __forceinline__ float tone_mag(const float2* z, const float2* w32, int i0, int t) {
     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll 8
     for (int m = 0; m < 32; ++m) {
-        const float2 w = c_fine.w32[(t * m) & 31];
+        const float2 w = w32[(t * m) & 31];
         const float2 v = z[i0 + m];
         acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
         acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
@@ -167,36 +167,45 @@ __device__ __forceinline__ float tone_mag(const float2* z, int i0, int t) {
 
 __device__ __forceinline__ int clip_start(int i) { return max(0, min(FINE_N - 32, i)); }
 
-// middle-Costas score for a window start tb (receiver.py:203): g49[49] scratch, result broadcast through *res
-__device__ __forceinline__ float costas_score(const float2* z, int tb, float* g49, int tid) {
-    if (tid < 49) {
-        const int k = tid / 7, t = tid - 7 * k;
-        g49[tid] = tone_mag(z, clip_start(tb + 32 * (36 + k)), t);
+// Middle-Costas scores (receiver.py:203) for n_tb window starts tb0 + tstep*i, i < n_tb <= 8: every (start, symbol, tone)
+// magnitude is computed by one thread and weighted (+1 on the Costas tone, -1/6 elsewhere); warp i then sums its 49
+// terms with a shuffle tree and lane 0 stores score[i].  Ends with a CTA barrier; scores are read from shared memory.
+__device__ __forceinline__ void costas_scores(const float2* z, const float2* w32, int tb0, int tstep, int n_tb, float* g49,
+                                              float* score, int tid) {
+    for (int i = tid; i < n_tb * 49; i += FINE_NT) {
+        const int ti = i / 49, r = i - 49 * ti;
+        const int k = r / 7, t = r - 7 * k;
+        const float g = tone_mag(z, w32, clip_start(tb0 + tstep * ti + 32 * (36 + k)), t);
+        g49[i] = (t == c_costas[k]) ? g : g * (-1.0f / 6.0f);
     }
     __syncthreads();
-    float s = 0.f;
-    for (int i = 0; i < 49; ++i) {
-        const int k = i / 7, t = i - 7 * k;
-        s = fmaf(g49[i], (t == c_costas[k]) ? 1.0f : (-1.0f / 6.0f), s);
+    const int w = tid >> 5, lane = tid & 31;
+    if (w < n_tb) {
+        float s = g49[w * 49 + lane] + ((lane + 32 < 49) ? g49[w * 49 + lane + 32] : 0.0f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) score[w] = s;
     }
     __syncthreads();
-    return s;      // every thread computes the same value
 }
 
-constexpr int FINE_SMEM_BYTES = 2 * FINE_N * (int)sizeof(float2) + 79 * 8 * (int)sizeof(float) + 8 * 49 * (int)sizeof(float);
+constexpr int FINE_SMEM_BYTES = 2 * FINE_N * (int)sizeof(float2) + (79 * 8 + 8 * 49 + 16) * (int)sizeof(float) + 32 * (int)sizeof(float2);
 
 // One CTA per work item (grid-stride over list[0..*count)).  cand arrays are indexed by the global slot id.
 // spec: [B][spec_stride] float2.  Outputs per slot: fo[slot], llr_fine[slot][174], optional sig_grid[slot][79][8].
-__global__ void __launch_bounds__(FINE_NT)
+__global__ void __launch_bounds__(FINE_NT, 2)
 k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restrict__ list, const int32_t* __restrict__ count,
        int n_direct, const int32_t* __restrict__ cycle_of, const int16_t* __restrict__ cand_f0,
        const int16_t* __restrict__ cand_h0, const float2* __restrict__ W3200, FineOut* __restrict__ fo,
        float* __restrict__ llr_fine, float* __restrict__ sig_grid) {
     extern __shared__ float2 fine_smem[];
-    float2* zb[2] = {fine_smem, fine_smem + FINE_N};
     float* G = reinterpret_cast<float*>(fine_smem + 2 * FINE_N);      // [79][8]
     float* g49 = G + 79 * 8;                                          // [8][49]
+    float* score = g49 + 8 * 49;                                      // [16]
+    float2* w32 = reinterpret_cast<float2*>(score + 16);              // [32]
     const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32) w32[tid] = c_fine.w32[tid];
+    __syncthreads();
     const int n_items = list ? *count : n_direct;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int slot = list ? list[item] : item;
@@ -205,41 +214,36 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         const float2* sp = spec + (size_t)cyc * spec_stride;
         const int fb0 = 50 * f0;                                   // int(0.5 + 16*fHz), fHz = 3.125*f0
         const int tb0 = (h0 >= 0) ? 8 * h0 : 8 * h0 + 1;           // int(0.5 + 200*tsec) truncates toward zero
-        // ---- time scan at ftweak = 0
-        fine_ifft(zb[0], sp, fb0, tid, W3200);
-        for (int i = tid; i < 8 * 49; i += FINE_NT) {
-            const int ti = i / 49, r = i - 49 * ti;
-            const int k = r / 7, t = r - 7 * k;
-            g49[i] = tone_mag(zb[0], clip_start(tb0 + (-8 + 2 * ti) + 32 * (36 + k)), t);
-        }
-        __syncthreads();
+        // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT
+        fine_ifft(fine_smem, sp, fb0, tid, W3200);
+        costas_scores(fine_smem, w32, tb0 - 8, 2, 8, g49, score, tid);
         int tt = -8;
         {
-            float best = 0.f;
-            for (int ti = 0; ti < 8; ++ti) {
-                float s = 0.f;
-                for (int i = 0; i < 49; ++i) {
-                    const int k = i / 7, t = i - 7 * k;
-                    s = fmaf(g49[ti * 49 + i], (t == c_costas[k]) ? 1.0f : (-1.0f / 6.0f), s);
-                }
-                if (ti == 0 || s > best) { best = s; tt = -8 + 2 * ti; }
-            }
+            float best = score[0];
+            for (int ti = 1; ti < 8; ++ti) if (score[ti] > best) { best = score[ti]; tt = -8 + 2 * ti; }   // first maximum
         }
+        // ---- frequency scan at the chosen time tweak (receiver.py:154-159).  The ftweak = 0 baseband is the one already
+        // in buffer 0, so it is scored first and the other 8 are computed into whichever buffer does not hold the best
+        // so far; "first maximum in ascending ftweak order" = larger score, or equal score and smaller index.
         __syncthreads();
-        // ---- frequency scan at the chosen time tweak; keep the best baseband in zb[keep]
-        int keep = 0, ff = -32;
-        float bestf = 0.f;
-        for (int fi = 0; fi < 9; ++fi) {
-            const int cur = (fi == 0) ? 0 : (keep ^ 1);
-            fine_ifft(zb[cur], sp, fb0 + (-32 + 8 * fi), tid, W3200);
-            const float s = costas_score(zb[cur], tb0 + tt, g49, tid);
-            if (fi == 0 || s > bestf) { bestf = s; ff = -32 + 8 * fi; keep = cur; }
+        costas_scores(fine_smem, w32, tb0 + tt, 0, 1, g49, score + 8, tid);
+        int keep = 0, best_fi = 4;
+        float bestf = score[8];
+        for (int q = 0; q < 8; ++q) {
+            const int fi = q < 4 ? q : q + 1;
+            const int cur = keep ^ 1;
+            __syncthreads();
+            fine_ifft(fine_smem + cur * FINE_N, sp, fb0 + (-32 + 8 * fi), tid, W3200);
+            costas_scores(fine_smem + cur * FINE_N, w32, tb0 + tt, 0, 1, g49, score + 8, tid);
+            const float sc = score[8];
+            if (sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; keep = cur; }
         }
-        // ---- final grid from the kept baseband
-        const float2* z = zb[keep];
+        const int ff = -32 + 8 * best_fi;
+        // ---- final grid from the kept baseband (receiver.py:161)
+        const float2* z = fine_smem + keep * FINE_N;
         for (int i = tid; i < 79 * 8; i += FINE_NT) {
             const int j = i >> 3, t = i & 7;
-            G[i] = tone_mag(z, clip_start(tb0 + tt + 32 * j), t);
+            G[i] = tone_mag(z, w32, clip_start(tb0 + tt + 32 * j), t);
         }
         __syncthreads();
         if (sig_grid) for (int i = tid; i < 79 * 8; i += FINE_NT) sig_grid[(size_t)slot * 632 + i] = G[i];

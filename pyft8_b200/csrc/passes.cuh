@@ -242,14 +242,11 @@ k_osd_items(CandState cs, const int32_t* __restrict__ list, const int32_t* __res
         const int slot = list[item / 10], k = item % 10;
         int found = 0;
         uint32_t bits[3] = {0, 0, 0};
-        if (k < 5) {
-            apply_ap(sm.llr[wi], cs.llr_fine + (size_t)slot * 174, k, lane);
-            found = osd_warp(sm.w[wi], sm.llr[wi], lane, S, D, bits);
-            ++n_osd;
-        } else if (k - 5 < cs.saved_n[slot]) {
-            const float* src = cs.saved_llr + ((size_t)slot * 5 + (k - 5)) * 174;
-            for (int i = lane; i < 174; i += 32) sm.llr[wi][i] = src[i];
-            __syncwarp();
+        const bool run = (k < 5) || (k - 5 < cs.saved_n[slot]);
+        if (run) {
+            // attempts 0..4: Candidate._set_AP pattern on the fine llr; 5..9: llr saved after a failed LDPC(90,20)
+            const float* src = (k < 5) ? cs.llr_fine + (size_t)slot * 174 : cs.saved_llr + ((size_t)slot * 5 + (k - 5)) * 174;
+            apply_ap(sm.llr[wi], src, (k < 5) ? k : 0, lane);
             found = osd_warp(sm.w[wi], sm.llr[wi], lane, S, D, bits);
             ++n_osd;
         }
