@@ -243,4 +243,21 @@ __device__ __forceinline__ void pass_inplace_batched(float2* buf, int tid, const
     __syncthreads();
 }
 
+// Out-of-place pass src -> dst (both shared memory, distinct): one butterfly at a time per thread (low register
+// pressure), a single barrier at the end.
+template <int N, int R, int S, int NT, bool INV>
+__device__ __forceinline__ void pass_oop(const float2* src, float2* dst, int lt, const float2* __restrict__ W) {
+    constexpr int NBF = N / R;
+#pragma unroll
+    for (int t0 = 0; t0 < NBF; t0 += NT) {
+        const int t = t0 + lt;
+        if (NBF % NT == 0 || t < NBF) {
+            float2 a[R];
+            Pass<N, R, S>::load(src, t, a);
+            Pass<N, R, S>::template compute_store<INV>(dst, t, a, W);
+        }
+    }
+    __syncthreads();
+}
+
 }  // namespace ft8

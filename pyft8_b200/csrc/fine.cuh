@@ -117,39 +117,50 @@ struct FineOut {               // per candidate
     int32_t snr;
 };
 
-// first inverse pass (R=5, S=1, M=640) with operands gathered from the cycle spectrum:
-// a[i] = spec[fb + i] for i < 850 (taper on [750,850)), spec[fb + i - 3200] for i >= 3050 (taper on [3050,3150)), else 0
-__device__ __forceinline__ float2 fine_band_at(const float2* __restrict__ spec, int fb, int i) {
-    if (i < 850) {
-        float2 v = __ldg(&spec[fb + i]);
-        if (i >= 750) { const float t = c_fine.taper[i - 750]; v.x *= t; v.y *= t; }
-        return v;
-    }
-    if (i >= 3050) {
-        float2 v = __ldg(&spec[fb + i - 3200]);
-        if (i < 3150) { const float t = c_fine.taper[i - 3050]; v.x *= t; v.y *= t; }
-        return v;
-    }
-    return make_float2(0.f, 0.f);
-}
-
-__device__ __forceinline__ void fine_ifft(float2* buf, const float2* __restrict__ spec, int fb, int tid,
-                                          const float2* __restrict__ W3200) {
-    constexpr int NBF = 640, PER = (NBF + FINE_NT - 1) / FINE_NT;
+// Inverse 3200-point FFT of the tapered band around fb (receiver.py:180-186), result in `dst`, `tmp` is scratch.
+// Band layout after the reference's roll(-150): a[i] = spec[fb + i] for i < 850 (taper on [750,850)),
+// spec[fb + i - 3200] for i >= 3050 (taper on [3050,3150)), zero elsewhere.  First pass (R=5, S=1, M=640) reads the
+// operands a[p + 640 j] straight from the spectrum: j = 2, 3 are always zero, j = 1 is non-zero only for p < 210 and
+// j = 4 only for p >= 490, so the radix-5 butterfly degenerates to b_k = a0 + a1 w^k + a4 conj(w^k), w = e^{+2 pi i/5}.
+__device__ __forceinline__ void fine_ifft(float2* dst, float2* tmp, const float2* __restrict__ spec, int fb, int tid,
+                                          const float2* __restrict__ W3200, const float* taper) {
+    constexpr int NBF = 640;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int p = tid + i * FINE_NT;
+    for (int p0 = 0; p0 < NBF; p0 += FINE_NT) {
+        const int p = p0 + tid;
         if (p < NBF) {
-            float2 a[5];
+            float2 a0 = __ldg(&spec[fb + p]);                       // i = p < 640: inside [0,850), taper-free
+            float2 b[5] = {a0, a0, a0, a0, a0};
+            if (p < 210) {                                          // i = p + 640 in [640, 850)
+                float2 a1 = __ldg(&spec[fb + p + 640]);
+                if (p >= 110) { const float t = taper[p - 110]; a1.x *= t; a1.y *= t; }
+                const float2 w1 = make_float2(0.30901699437494742410f, 0.95105651629515357212f);
+                const float2 w2 = make_float2(-0.80901699437494742410f, 0.58778525229247312917f);
+                b[0] = cadd(a0, a1);
+                b[1] = cadd(a0, cmul(a1, w1));
+                b[2] = cadd(a0, cmul(a1, w2));
+                b[3] = cadd(a0, cmulc(a1, w2));
+                b[4] = cadd(a0, cmulc(a1, w1));
+            } else if (p >= 490) {                                  // i = p + 2560 in [3050, 3200)
+                float2 a4 = __ldg(&spec[fb + p - 640]);
+                if (p < 590) { const float t = taper[p - 490]; a4.x *= t; a4.y *= t; }
+                const float2 w1 = make_float2(0.30901699437494742410f, 0.95105651629515357212f);
+                const float2 w2 = make_float2(-0.80901699437494742410f, 0.58778525229247312917f);
+                b[0] = cadd(a0, a4);
+                b[1] = cadd(a0, cmulc(a4, w1));
+                b[2] = cadd(a0, cmulc(a4, w2));
+                b[3] = cadd(a0, cmul(a4, w2));
+                b[4] = cadd(a0, cmul(a4, w1));
+            }
+            tmp[5 * p] = b[0];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) a[j] = fine_band_at(spec, fb, p + 640 * j);
-            Pass<3200, 5, 1>::template compute_store<true>(buf, p, a, W3200);
+            for (int k = 1; k < 5; ++k) tmp[5 * p + k] = cmulc(b[k], __ldg(&W3200[p * k]));
         }
     }
     __syncthreads();
-    pass_inplace<3200, 5, 5, FINE_NT, true>(buf, tid, W3200, CtaSync());
-    pass_inplace<3200, 8, 25, FINE_NT, true>(buf, tid, W3200, CtaSync());
-    pass_inplace<3200, 16, 200, FINE_NT, true>(buf, tid, W3200, CtaSync());
+    pass_oop<3200, 5, 5, FINE_NT, true>(tmp, dst, tid, W3200);
+    pass_oop<3200, 8, 25, FINE_NT, true>(dst, tmp, tid, W3200);
+    pass_oop<3200, 16, 200, FINE_NT, true>(tmp, dst, tid, W3200);
 }
 
 // |DFT32(z[i0 : i0+32])[t]| / 3200  (numpy's ifft carries the 1/N).  w32 = shared copy of exp(-2 pi i m / 32).
@@ -189,7 +200,7 @@ __device__ __forceinline__ void costas_scores(const float2* z, const float2* w32
     __syncthreads();
 }
 
-constexpr int FINE_SMEM_BYTES = 2 * FINE_N * (int)sizeof(float2) + (79 * 8 + 8 * 49 + 16) * (int)sizeof(float) + 32 * (int)sizeof(float2);
+constexpr int FINE_SMEM_BYTES = 3 * FINE_N * (int)sizeof(float2) + (79 * 8 + 8 * 49 + 16 + 100) * (int)sizeof(float) + 32 * (int)sizeof(float2);
 
 // One CTA per work item (grid-stride over list[0..*count)).  cand arrays are indexed by the global slot id.
 // spec: [B][spec_stride] float2.  Outputs per slot: fo[slot], llr_fine[slot][174], optional sig_grid[slot][79][8].
@@ -199,12 +210,14 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
        const int16_t* __restrict__ cand_h0, const float2* __restrict__ W3200, FineOut* __restrict__ fo,
        float* __restrict__ llr_fine, float* __restrict__ sig_grid) {
     extern __shared__ float2 fine_smem[];
-    float* G = reinterpret_cast<float*>(fine_smem + 2 * FINE_N);      // [79][8]
+    float* G = reinterpret_cast<float*>(fine_smem + 3 * FINE_N);      // [79][8]
     float* g49 = G + 79 * 8;                                          // [8][49]
     float* score = g49 + 8 * 49;                                      // [16]
-    float2* w32 = reinterpret_cast<float2*>(score + 16);              // [32]
+    float* taper = score + 16;                                        // [100]
+    float2* w32 = reinterpret_cast<float2*>(taper + 100);             // [32]
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < 32) w32[tid] = c_fine.w32[tid];
+    if (tid < 100) taper[tid] = c_fine.taper[tid];
     __syncthreads();
     const int n_items = list ? *count : n_direct;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -215,7 +228,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         const int fb0 = 50 * f0;                                   // int(0.5 + 16*fHz), fHz = 3.125*f0
         const int tb0 = (h0 >= 0) ? 8 * h0 : 8 * h0 + 1;           // int(0.5 + 200*tsec) truncates toward zero
         // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT
-        fine_ifft(fine_smem, sp, fb0, tid, W3200);
+        fine_ifft(fine_smem, fine_smem + FINE_N, sp, fb0, tid, W3200, taper);
         costas_scores(fine_smem, w32, tb0 - 8, 2, 8, g49, score, tid);
         int tt = -8;
         {
@@ -231,9 +244,9 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         float bestf = score[8];
         for (int q = 0; q < 8; ++q) {
             const int fi = q < 4 ? q : q + 1;
-            const int cur = keep ^ 1;
+            const int cur = (keep + 1) % 3, scratch = (keep + 2) % 3;       // the three buffers rotate around the best one
             __syncthreads();
-            fine_ifft(fine_smem + cur * FINE_N, sp, fb0 + (-32 + 8 * fi), tid, W3200);
+            fine_ifft(fine_smem + cur * FINE_N, fine_smem + scratch * FINE_N, sp, fb0 + (-32 + 8 * fi), tid, W3200, taper);
             costas_scores(fine_smem + cur * FINE_N, w32, tb0 + tt, 0, 1, g49, score + 8, tid);
             const float sc = score[8];
             if (sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; keep = cur; }

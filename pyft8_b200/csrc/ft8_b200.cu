@@ -63,6 +63,7 @@ struct ft8_handle {
     cudaEvent_t ev[12] = {};          // ev[0..8]: stage boundaries of ft8_decode_cycles; ev[10], ev[11]: stand-alone ops
     float last_ms[9] = {};            // see ft8_last_kernel_ms
     ft8_stats stats{};
+    std::vector<int32_t> host_offs, host_idx, host_cur;   // host-side ordering scratch
 };
 
 #define CK(call)                                                                                   \
@@ -715,31 +716,52 @@ extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dty
     CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[8]));
     for (int i = 1; i <= 8; ++i) CK(cudaEventElapsedTime(&h->last_ms[i], h->ev[i - 1], h->ev[i]));
     // emission order (receiver.py:389-398): pass by pass; inside a pass by llr_sd descending (the fine sd from
-    // ipass 2 on, all-equal before), ties by candidate rank; then de-dup on the payload (receiver.py:53-55)
-    std::sort(h->h_rec, h->h_rec + nrec, [](const ft8_record& a, const ft8_record& b) {
-        if (a.cycle != b.cycle) return a.cycle < b.cycle;
-        if (a.ipass != b.ipass) return a.ipass < b.ipass;
-        if (a.ipass >= 2 && a.fine_sd != b.fine_sd) return a.fine_sd > b.fine_sd;
-        return a.cand < b.cand;
-    });
-    for (int b = 0; b < B; ++b) n_rec[b] = 0;
+    // ipass 2 on, all-equal before), ties by candidate rank; then de-dup on the payload (receiver.py:53-55).
+    // Records arrive in atomic-append order: bucket by cycle (counting sort), then order each cycle's few dozen records.
+    std::vector<int32_t>& offs = h->host_offs;
+    std::vector<int32_t>& idx = h->host_idx;
+    offs.assign((size_t)B + 1, 0);
+    idx.resize((size_t)std::max(nrec, 1));
+    for (int i = 0; i < nrec; ++i) offs[h->h_rec[i].cycle + 1]++;
+    for (int b = 0; b < B; ++b) offs[b + 1] += offs[b];
+    {
+        std::vector<int32_t>& cur = h->host_cur;
+        cur.assign(offs.begin(), offs.end() - 1);
+        for (int i = 0; i < nrec; ++i) idx[cur[h->h_rec[i].cycle]++] = i;
+    }
+    const ft8_record* R = h->h_rec;
     int64_t emitted = 0;
-    int written = 0, i = 0;
+    int written = 0;
     bool overflow = false;
-    while (i < nrec) {
-        int j = i;
-        while (j < nrec && h->h_rec[j].cycle == h->h_rec[i].cycle) ++j;
-        for (int a = i; a < j; ++a) {
-            ft8_record& r = h->h_rec[a];
+    constexpr int HT = 1024;                       // per-cycle open-addressed set of payloads (<= 928 records per cycle)
+    int32_t ht[HT];
+    for (int b = 0; b < B; ++b) {
+        n_rec[b] = 0;
+        int32_t* lo = idx.data() + offs[b];
+        int32_t* hi = idx.data() + offs[b + 1];
+        if (lo == hi) continue;
+        std::sort(lo, hi, [R](int32_t x, int32_t y) {
+            const ft8_record &a = R[x], &c = R[y];
+            if (a.ipass != c.ipass) return a.ipass < c.ipass;
+            if (a.ipass >= 2 && a.fine_sd != c.fine_sd) return a.fine_sd > c.fine_sd;
+            return a.cand < c.cand;
+        });
+        for (int i = 0; i < HT; ++i) ht[i] = -1;
+        for (int32_t* it = lo; it != hi; ++it) {
+            ft8_record r = R[*it];
+            const uint32_t w2 = r.bits91[2] & 0x1FFFu;           // payload = bits 0..76
+            uint32_t hsh = (r.bits91[0] * 0x9E3779B1u) ^ (r.bits91[1] * 0x85EBCA77u) ^ (w2 * 0xC2B2AE3Du);
+            hsh = (hsh ^ (hsh >> 15)) & (HT - 1);
             r.emitted = 1;
-            for (int c = i; c < a; ++c) {
-                const ft8_record& q = h->h_rec[c];
-                if (q.bits91[0] == r.bits91[0] && q.bits91[1] == r.bits91[1] && ((q.bits91[2] ^ r.bits91[2]) & 0x1FFFu) == 0) { r.emitted = 0; break; }
+            while (ht[hsh] >= 0) {
+                const ft8_record& q = R[ht[hsh]];
+                if (q.bits91[0] == r.bits91[0] && q.bits91[1] == r.bits91[1] && (q.bits91[2] & 0x1FFFu) == w2) { r.emitted = 0; break; }
+                hsh = (hsh + 1) & (HT - 1);
             }
+            if (r.emitted) ht[hsh] = *it;
             emitted += r.emitted;
-            if (written < rec_capacity) { rec[written++] = r; n_rec[r.cycle]++; } else overflow = true;
+            if (written < rec_capacity) { rec[written++] = r; n_rec[b]++; } else overflow = true;
         }
-        i = j;
     }
     ft8_stats& s = h->stats;
     memset(&s, 0, sizeof(s));
