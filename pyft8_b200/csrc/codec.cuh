@@ -36,15 +36,29 @@ __device__ __forceinline__ bool crc_ok_serial(const uint32_t* w) {
     return syn == 0;
 }
 
-// Warp-cooperative version: every lane passes the same three words.
-__device__ __forceinline__ bool crc_ok_warp(uint32_t w0, uint32_t w1, uint32_t w2, int lane) {
+// Per-lane copy of the syndrome table: lane l keeps the contributions of codeword bits l, 32+l, 64+l in registers
+// (a lane-indexed read of __constant__ memory would serialise 32 ways).
+struct LaneSyn { uint32_t s0, s1, s2; };
+__device__ __forceinline__ LaneSyn load_lane_syn(int lane) {
+    LaneSyn r;
+    r.s0 = c_codec.crc_syn[lane];
+    r.s1 = c_codec.crc_syn[32 + lane];
+    r.s2 = (lane < 27) ? c_codec.crc_syn[64 + lane] : 0u;
+    return r;
+}
+
+// CRC syndrome of a 91-bit word held identically by every lane (14 bits; 0 = CRC matches)
+__device__ __forceinline__ uint32_t syndrome_warp(uint32_t w0, uint32_t w1, uint32_t w2, int lane, const LaneSyn& ls) {
+    uint32_t syn = ((w0 >> lane) & 1u) ? ls.s0 : 0u;
+    syn ^= ((w1 >> lane) & 1u) ? ls.s1 : 0u;
+    syn ^= ((w2 >> lane) & 1u) ? ls.s2 : 0u;
+    return __reduce_xor_sync(0xffffffffu, syn);
+}
+
+// Warp-cooperative CRC check: every lane passes the same three words.
+__device__ __forceinline__ bool crc_ok_warp(uint32_t w0, uint32_t w1, uint32_t w2, int lane, const LaneSyn& ls) {
     if ((w0 | w1 | (w2 & 0x1FFFu)) == 0) return false;
-    uint32_t syn = 0;
-    if ((w0 >> lane) & 1u) syn ^= c_codec.crc_syn[lane];
-    if ((w1 >> lane) & 1u) syn ^= c_codec.crc_syn[32 + lane];
-    if (lane < 27 && ((w2 >> lane) & 1u)) syn ^= c_codec.crc_syn[64 + lane];
-    syn = __reduce_xor_sync(0xffffffffu, syn);
-    return syn == 0;
+    return syndrome_warp(w0, w1, w2, lane, ls) == 0;
 }
 
 // decoders.py:70-115 as accept/reject for one 29-bit call field.

@@ -163,41 +163,54 @@ __device__ __forceinline__ void fine_ifft(float2* dst, float2* tmp, const float2
     pass_oop<3200, 16, 200, FINE_NT, true>(tmp, dst, tid, W3200);
 }
 
-// |DFT32(z[i0 : i0+32])[t]| / 3200  (numpy's ifft carries the 1/N).  w32 = shared copy of exp(-2 pi i m / 32).
-__device__ __forceinline__ float tone_mag(const float2* z, const float2* w32, int i0, int t) {
-    float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 8
-    for (int m = 0; m < 32; ++m) {
-        const float2 w = w32[(t * m) & 31];
-        const float2 v = z[i0 + m];
-        acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
-        acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
+// 32-sample symbol DFT by one warp (receiver.py:195): lane m holds z[i0+m] and its twiddles tw[t] = exp(-2 pi i t m/32),
+// t < 8.  The 8 partial products are summed over the 32 lanes with a halving exchange (each step keeps half of the bins),
+// 18 shuffles instead of 80.  Returns |bin| / 3200 (numpy's ifft carries the 1/N) for bin = 4*bit4 + 2*bit3 + bit2 of the lane index;
+// the four lanes that share lane>>2 hold the same value.
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int o) {
+    return make_float2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
+}
+
+__device__ __forceinline__ float dft32_mag(const float2* z, int i0, int lane, const float2 (&tw)[8]) {
+    const float2 v = z[i0 + lane];
+    float2 c[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) c[t] = cmul(v, tw[t]);
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float2 d4[4], d2[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                       // lanes with bit 4 clear keep bins 0..3, the others 4..7
+        const float2 send = h16 ? c[j] : c[j + 4], keep = h16 ? c[j + 4] : c[j];
+        d4[j] = cadd(keep, shfl_xor2(send, 16));
     }
-    return sqrtf(fmaf(acc.x, acc.x, acc.y * acc.y)) * (1.0f / 3200.0f);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float2 send = h8 ? d4[j] : d4[j + 2], keep = h8 ? d4[j + 2] : d4[j];
+        d2[j] = cadd(keep, shfl_xor2(send, 8));
+    }
+    float2 s;
+    {
+        const float2 send = h4 ? d2[0] : d2[1], keep = h4 ? d2[1] : d2[0];
+        s = cadd(keep, shfl_xor2(send, 4));
+    }
+    s = cadd(s, shfl_xor2(s, 2));
+    s = cadd(s, shfl_xor2(s, 1));
+    return sqrtf(fmaf(s.x, s.x, s.y * s.y)) * (1.0f / 3200.0f);
 }
 
 __device__ __forceinline__ int clip_start(int i) { return max(0, min(FINE_N - 32, i)); }
 
-// Middle-Costas scores (receiver.py:203) for n_tb window starts tb0 + tstep*i, i < n_tb <= 8: every (start, symbol, tone)
-// magnitude is computed by one thread and weighted (+1 on the Costas tone, -1/6 elsewhere); warp i then sums its 49
-// terms with a shuffle tree and lane 0 stores score[i].  Ends with a CTA barrier; scores are read from shared memory.
-__device__ __forceinline__ void costas_scores(const float2* z, const float2* w32, int tb0, int tstep, int n_tb, float* g49,
-                                              float* score, int tid) {
-    for (int i = tid; i < n_tb * 49; i += FINE_NT) {
-        const int ti = i / 49, r = i - 49 * ti;
-        const int k = r / 7, t = r - 7 * k;
-        const float g = tone_mag(z, w32, clip_start(tb0 + tstep * ti + 32 * (36 + k)), t);
-        g49[i] = (t == c_costas[k]) ? g : g * (-1.0f / 6.0f);
-    }
-    __syncthreads();
-    const int w = tid >> 5, lane = tid & 31;
-    if (w < n_tb) {
-        float s = g49[w * 49 + lane] + ((lane + 32 < 49) ? g49[w * 49 + lane + 32] : 0.0f);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) score[w] = s;
-    }
-    __syncthreads();
+// Weighted Costas contribution of symbol row k (middle block) for a window start tb: sum over tones 0..6 of
+// |bin| * (+1 on the Costas tone, -1/6 elsewhere), every lane gets the row total (receiver.py:198-203).
+__device__ __forceinline__ float costas_row(const float2* z, int tb, int k, int lane, const float2 (&tw)[8]) {
+    const float g = dft32_mag(z, clip_start(tb + 32 * (36 + k)), lane, tw);
+    const int bin = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    float c = 0.0f;
+    if ((lane & 3) == 0 && bin < 7) c = (bin == c_costas[k]) ? g : g * (-1.0f / 6.0f);
+    c += __shfl_xor_sync(0xffffffffu, c, 16);
+    c += __shfl_xor_sync(0xffffffffu, c, 8);
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    return c;                                           // lanes with (lane & 3) == 0 hold the total
 }
 
 constexpr int FINE_SMEM_BYTES = 3 * FINE_N * (int)sizeof(float2) + (79 * 8 + 8 * 49 + 16 + 100) * (int)sizeof(float) + 32 * (int)sizeof(float2);
@@ -215,10 +228,13 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
     float* score = g49 + 8 * 49;                                      // [16]
     float* taper = score + 16;                                        // [100]
     float2* w32 = reinterpret_cast<float2*>(taper + 100);             // [32]
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 32) w32[tid] = c_fine.w32[tid];
     if (tid < 100) taper[tid] = c_fine.taper[tid];
     __syncthreads();
+    float2 tw[8];                                                     // this lane's DFT32 twiddles, fixed for the kernel
+#pragma unroll
+    for (int t = 0; t < 8; ++t) tw[t] = w32[(t * lane) & 31];
     const int n_items = list ? *count : n_direct;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int slot = list ? list[item] : item;
@@ -227,9 +243,15 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         const float2* sp = spec + (size_t)cyc * spec_stride;
         const int fb0 = 50 * f0;                                   // int(0.5 + 16*fHz), fHz = 3.125*f0
         const int tb0 = (h0 >= 0) ? 8 * h0 : 8 * h0 + 1;           // int(0.5 + 200*tsec) truncates toward zero
-        // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT
+        // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT; warp w scores start w
         fine_ifft(fine_smem, fine_smem + FINE_N, sp, fb0, tid, W3200, taper);
-        costas_scores(fine_smem, w32, tb0 - 8, 2, 8, g49, score, tid);
+        {
+            float sc = 0.0f;
+#pragma unroll 1
+            for (int k = 0; k < 7; ++k) sc += costas_row(fine_smem, tb0 - 8 + 2 * warp, k, lane, tw);
+            if (lane == 0) score[warp] = sc;
+        }
+        __syncthreads();
         int tt = -8;
         {
             float best = score[0];
@@ -238,25 +260,30 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         // ---- frequency scan at the chosen time tweak (receiver.py:154-159).  The ftweak = 0 baseband is the one already
         // in buffer 0, so it is scored first and the other 8 are computed into whichever buffer does not hold the best
         // so far; "first maximum in ascending ftweak order" = larger score, or equal score and smaller index.
-        __syncthreads();
-        costas_scores(fine_smem, w32, tb0 + tt, 0, 1, g49, score + 8, tid);
+        // Warp k (< 7) scores Costas symbol k; the 7 row totals are summed in order by every thread.
         int keep = 0, best_fi = 4;
-        float bestf = score[8];
-        for (int q = 0; q < 8; ++q) {
-            const int fi = q < 4 ? q : q + 1;
-            const int cur = (keep + 1) % 3, scratch = (keep + 2) % 3;       // the three buffers rotate around the best one
+        float bestf = 0.0f;
+        for (int q = -1; q < 8; ++q) {
+            const int fi = q < 0 ? 4 : (q < 4 ? q : q + 1);
+            const int cur = q < 0 ? 0 : (keep + 1) % 3, scratch = (keep + 2) % 3;   // the three buffers rotate around the best
+            if (q >= 0) fine_ifft(fine_smem + cur * FINE_N, fine_smem + scratch * FINE_N, sp, fb0 + (-32 + 8 * fi), tid, W3200, taper);
+            if (warp < 7) {
+                const float r = costas_row(fine_smem + cur * FINE_N, tb0 + tt, warp, lane, tw);
+                if (lane == 0) score[8 + warp] = r;
+            }
             __syncthreads();
-            fine_ifft(fine_smem + cur * FINE_N, fine_smem + scratch * FINE_N, sp, fb0 + (-32 + 8 * fi), tid, W3200, taper);
-            costas_scores(fine_smem + cur * FINE_N, w32, tb0 + tt, 0, 1, g49, score + 8, tid);
-            const float sc = score[8];
-            if (sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; keep = cur; }
+            float sc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) sc += score[8 + k];
+            if (q < 0 || sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; keep = cur; }
+            __syncthreads();
         }
         const int ff = -32 + 8 * best_fi;
-        // ---- final grid from the kept baseband (receiver.py:161)
+        // ---- final grid from the kept baseband (receiver.py:161): one warp per symbol row
         const float2* z = fine_smem + keep * FINE_N;
-        for (int i = tid; i < 79 * 8; i += FINE_NT) {
-            const int j = i >> 3, t = i & 7;
-            G[i] = tone_mag(z, w32, clip_start(tb0 + tt + 32 * j), t);
+        for (int j = warp; j < 79; j += FINE_NT / 32) {
+            const float g = dft32_mag(z, clip_start(tb0 + tt + 32 * j), lane, tw);
+            if ((lane & 3) == 0) G[j * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = g;
         }
         __syncthreads();
         if (sig_grid) for (int i = tid; i < 79 * 8; i += FINE_NT) sig_grid[(size_t)slot * 632 + i] = G[i];

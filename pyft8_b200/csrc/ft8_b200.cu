@@ -267,7 +267,7 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
     CKC(dmalloc(&h->d_saved_n, N)); CKC(dmalloc(&h->d_saved_ap, N * 5)); CKC(dmalloc(&h->d_bits, N * 3));
     CKC(dmalloc(&h->d_ripass, N)); CKC(dmalloc(&h->d_rap, N)); CKC(dmalloc(&h->d_rmethod, N)); CKC(dmalloc(&h->d_rnits, N));
     CKC(dmalloc(&h->d_osd_found, N * 10)); CKC(dmalloc(&h->d_osd_bits, N * 30));
-    CKC(dmalloc(&h->d_list_fine, N)); CKC(dmalloc(&h->d_list_osd, N)); CKC(dmalloc(&h->d_counts, 4));
+    CKC(dmalloc(&h->d_list_fine, N)); CKC(dmalloc(&h->d_list_osd, N)); CKC(dmalloc(&h->d_counts, 8));
     CKC(dmalloc(&h->d_stats, 1)); CKC(dmalloc(&h->d_rec, N));
     CKC(cudaMallocHost((void**)&h->h_rec, N * sizeof(ft8_record)));
     CKC(cudaMallocHost((void**)&h->h_counts, 4 * sizeof(int32_t)));
@@ -665,7 +665,7 @@ extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dty
     const void* da;
     TRY(stage_audio(h, audio, audio_dtype, B, mem, &da));
     int launches = 0;
-    CK(cudaMemsetAsync(h->d_counts, 0, 4 * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(h->d_counts, 0, 8 * sizeof(int32_t), h->stream));   // [0] fine list, [1] osd list, [2] records, [4],[5] work cursors
     CK(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), h->stream));
     CK(cudaEventRecord(h->ev[0], h->stream));
     // S1
@@ -692,12 +692,12 @@ extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dty
     CK(cudaEventRecord(h->ev[5], h->stream));
     // ipass 2-4
     k_pass234<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
-        cs, h->d_list_fine, h->d_counts + 0, h->cfg.llr_sd_min, h->d_list_osd, h->d_counts + 1, h->d_stats);
+        cs, h->d_list_fine, h->d_counts + 0, h->cfg.llr_sd_min, h->d_list_osd, h->d_counts + 1, h->d_counts + 4, h->d_stats);
     CK(cudaGetLastError()); ++launches;
     CK(cudaEventRecord(h->ev[6], h->stream));
     // ipass 5-6
     k_osd_items<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(OsdSmem), h->stream>>>(
-        cs, h->d_list_osd, h->d_counts + 1, h->cfg.osd_singleflips, h->cfg.osd_doubleflips, h->d_stats);
+        cs, h->d_list_osd, h->d_counts + 1, h->cfg.osd_singleflips, h->cfg.osd_doubleflips, h->d_counts + 5, h->d_stats);
     CK(cudaGetLastError()); ++launches;
     k_osd_resolve<<<persistent_blocks(h, 2), 128, 0, h->stream>>>(cs, h->d_list_osd, h->d_counts + 1, h->d_stats);
     CK(cudaGetLastError()); ++launches;

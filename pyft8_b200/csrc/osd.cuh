@@ -39,7 +39,7 @@ struct OsdWarpScratch {
 
 // Returns trial index + 1 of the first accepted trial word (0 = none); bits = that word.
 // llr: 174 floats in shared or global memory.
-__device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int lane, int S, int D, uint32_t* bits) {
+__device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int lane, const LaneSyn& ls, int S, int D, uint32_t* bits) {
     // ---- 1. reliability order by rank counting
     for (int i = lane; i < 174; i += 32) {
         const float a = fabsf(llr[i]);
@@ -107,41 +107,58 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int
             if (hb) { if (pw == 0) u0 |= pb; else if (pw == 1) u1 |= pb; else u2 |= pb; }
             if (lane == 0) s.piv_row[npiv] = (uint8_t)p;
             ++npiv;
+            // pw is warp-uniform: three copies of the update, each testing a fixed word
+            if (pw == 0) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const uint32_t w = (pw == 0) ? c0[k] : ((pw == 1) ? c1[k] : c2[k]);
-                if (w & pb) { c0[k] ^= m0; c1[k] ^= m1; c2[k] ^= m2; }
+                for (int k = 0; k < 6; ++k) if (c0[k] & pb) { c0[k] ^= m0; c1[k] ^= m1; c2[k] ^= m2; }
+            } else if (pw == 1) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) if (c1[k] & pb) { c0[k] ^= m0; c1[k] ^= m1; c2[k] ^= m2; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) if (c2[k] & pb) { c0[k] ^= m0; c1[k] ^= m1; c2[k] ^= m2; }
             }
         }
     }
     __syncwarp();
     // ---- 4. the 1+S vectors over the original columns 0..90, each with its CRC syndrome
+    // per slot: where its bit lands in the 91-bit word (one of three masks is non-zero; none for columns >= 91)
+    uint32_t om0[6], om1[6], om2[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const uint32_t c = orig[k];
+        const uint32_t bit = (c < 91) ? (1u << (c & 31)) : 0u;
+        om0[k] = (c < 32) ? bit : 0u;
+        om1[k] = (c >= 32 && c < 64) ? bit : 0u;
+        om2[k] = (c >= 64) ? bit : 0u;
+    }
     const int nvec = 1 + S;
     for (int vi = 0; vi < nvec; ++vi) {
-        uint32_t w0 = 0, w1 = 0, w2 = 0, syn = 0;
-        int prow = 0;
-        if (vi > 0) prow = s.piv_row[90 - (vi - 1)];
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        if (vi == 0) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            if (orig[k] < 91) {
-                uint32_t b;
-                if (vi == 0) b = (__popc(c0[k] & u0) + __popc(c1[k] & u1) + __popc(c2[k] & u2)) & 1u;
-                else {
-                    const uint32_t w = (prow < 32) ? c0[k] : ((prow < 64) ? c1[k] : c2[k]);
-                    b = (w >> (prow & 31)) & 1u;
-                }
-                if (b) {
-                    const uint32_t c = orig[k];
-                    const uint32_t bit = 1u << (c & 31);
-                    if (c < 32) w0 |= bit; else if (c < 64) w1 |= bit; else w2 |= bit;
-                    syn ^= c_codec.crc_syn[c];
-                }
+            for (int k = 0; k < 6; ++k) {
+                const uint32_t m = 0u - ((__popc(c0[k] & u0) + __popc(c1[k] & u1) + __popc(c2[k] & u2)) & 1u);
+                w0 |= om0[k] & m; w1 |= om1[k] & m; w2 |= om2[k] & m;
+            }
+        } else {
+            const int prow = s.piv_row[90 - (vi - 1)];
+            const int sh = prow & 31;
+            if (prow < 32) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { const uint32_t m = 0u - ((c0[k] >> sh) & 1u); w0 |= om0[k] & m; w1 |= om1[k] & m; w2 |= om2[k] & m; }
+            } else if (prow < 64) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { const uint32_t m = 0u - ((c1[k] >> sh) & 1u); w0 |= om0[k] & m; w1 |= om1[k] & m; w2 |= om2[k] & m; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { const uint32_t m = 0u - ((c2[k] >> sh) & 1u); w0 |= om0[k] & m; w1 |= om1[k] & m; w2 |= om2[k] & m; }
             }
         }
         w0 = __reduce_or_sync(0xffffffffu, w0);
         w1 = __reduce_or_sync(0xffffffffu, w1);
         w2 = __reduce_or_sync(0xffffffffu, w2);
-        syn = __reduce_xor_sync(0xffffffffu, syn);
+        const uint32_t syn = syndrome_warp(w0, w1, w2, lane, ls);
         if (lane == 0) { s.vec[vi][0] = w0; s.vec[vi][1] = w1; s.vec[vi][2] = w2; s.vec[vi][3] = syn; }
     }
     __syncwarp();

@@ -93,6 +93,7 @@ k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows
     load_ldpc_tables(sm.tab);
     __syncthreads();
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const LaneSyn ls = load_lane_syn(lane);
     LdpcWarpScratch& ws = sm.w[wi];
     float* llr0 = sm.llr0[wi];
     const int warps_total = gridDim.x * WARPS_PER_CTA;
@@ -131,13 +132,13 @@ k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows
         for (int ap = 0; ap < 5 && !done; ++ap) {
             apply_ap(ws.llr, llr0, ap, lane);
             uint32_t bits[3];
-            if (good91_warp(ws.llr, lane, bits)) {
+            if (good91_warp(ws.llr, lane, bits, ls)) {
                 if (lane == 0) set_result(cs, slot, bits, 0, ap, 0 /*GOOD91*/, 0);
                 done = true;
                 break;
             }
             int nits, iters = 0;
-            const int st = ldpc_warp(ws, sm.tab, lane, 35, 5, nits, bits, iters);
+            const int st = ldpc_warp(ws, sm.tab, lane, ls, 35, 5, nits, bits, iters);
             ++n_ldpc; n_iter += iters;
             if (st == 1) {
                 if (lane == 0) set_result(cs, slot, bits, 0, ap, 1 /*LDPC5*/, nits);
@@ -159,18 +160,26 @@ k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows
 // ipass 2..4 over list_fine.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_pass234(CandState cs, const int32_t* __restrict__ list, const int32_t* __restrict__ count, float sd_min,
-          int32_t* __restrict__ list_osd, int32_t* __restrict__ count_osd, DevStats* __restrict__ stats) {
+          int32_t* __restrict__ list_osd, int32_t* __restrict__ count_osd, int32_t* __restrict__ next_item,
+          DevStats* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char pass_smem_raw[];
     PassSmem& sm = *reinterpret_cast<PassSmem*>(pass_smem_raw);
     load_ldpc_tables(sm.tab);
     __syncthreads();
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const LaneSyn ls = load_lane_syn(lane);
     LdpcWarpScratch& ws = sm.w[wi];
     float* llr0 = sm.llr0[wi];
     const int warps_total = gridDim.x * WARPS_PER_CTA;
     const int n_items = *count;
     unsigned long long n_ldpc = 0, n_iter = 0, n_dec = 0, n_fpass = 0, n_feval = 0;
-    for (int item = blockIdx.x * WARPS_PER_CTA + wi; item < n_items; item += warps_total) {
+    (void)warps_total;
+    // work is very uneven (0 .. 110 LDPC iterations per candidate): warps pull items from a device counter
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(next_item, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
         const int slot = list[item];
         const FineOut fo = cs.fine[slot];
         ++n_feval;
@@ -185,7 +194,7 @@ k_pass234(CandState cs, const int32_t* __restrict__ list, const int32_t* __restr
         uint32_t bits[3];
         for (int ap = 0; ap < 2 && !done; ++ap) {             // ipass 2
             apply_ap(ws.llr, llr0, ap, lane);
-            if (good91_warp(ws.llr, lane, bits)) {
+            if (good91_warp(ws.llr, lane, bits, ls)) {
                 if (lane == 0) set_result(cs, slot, bits, 2, ap, 0, 0);
                 done = true;
             }
@@ -193,7 +202,7 @@ k_pass234(CandState cs, const int32_t* __restrict__ list, const int32_t* __restr
         for (int ap = 0; ap < 2 && !done; ++ap) {             // ipass 3
             apply_ap(ws.llr, llr0, ap, lane);
             int nits, iters = 0;
-            const int st = ldpc_warp(ws, sm.tab, lane, 35, 5, nits, bits, iters);
+            const int st = ldpc_warp(ws, sm.tab, lane, ls, 35, 5, nits, bits, iters);
             ++n_ldpc; n_iter += iters;
             if (st == 1) { if (lane == 0) set_result(cs, slot, bits, 3, ap, 1, nits); done = true; }
         }
@@ -201,7 +210,7 @@ k_pass234(CandState cs, const int32_t* __restrict__ list, const int32_t* __restr
         for (int ap = 0; ap < 5 && !done; ++ap) {             // ipass 4
             apply_ap(ws.llr, llr0, ap, lane);
             int nits, iters = 0;
-            const int st = ldpc_warp(ws, sm.tab, lane, 90, 20, nits, bits, iters);
+            const int st = ldpc_warp(ws, sm.tab, lane, ls, 90, 20, nits, bits, iters);
             ++n_ldpc; n_iter += iters;
             if (st == 1) { if (lane == 0) set_result(cs, slot, bits, 4, ap, 2, nits); done = true; }
             else if (st >= 2) {                               // FAIL or STALL: reference keeps the llr (receiver.py:128-129)
@@ -231,14 +240,20 @@ struct OsdSmem {
 // ipass 5-6: item = 10 * list index + attempt.  attempts 0..4: AP pattern on the fine llr; 5..9: saved llr.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_osd_items(CandState cs, const int32_t* __restrict__ list, const int32_t* __restrict__ count, int S, int D,
-            DevStats* __restrict__ stats) {
+            int32_t* __restrict__ next_item, DevStats* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char pass_smem_raw[];
     OsdSmem& sm = *reinterpret_cast<OsdSmem*>(pass_smem_raw);
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const LaneSyn ls = load_lane_syn(lane);
     const int warps_total = gridDim.x * WARPS_PER_CTA;
     const int n_items = *count * 10;
     unsigned long long n_osd = 0;
-    for (int item = blockIdx.x * WARPS_PER_CTA + wi; item < n_items; item += warps_total) {
+    (void)warps_total;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(next_item, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
         const int slot = list[item / 10], k = item % 10;
         int found = 0;
         uint32_t bits[3] = {0, 0, 0};
@@ -247,7 +262,7 @@ k_osd_items(CandState cs, const int32_t* __restrict__ list, const int32_t* __res
             // attempts 0..4: Candidate._set_AP pattern on the fine llr; 5..9: llr saved after a failed LDPC(90,20)
             const float* src = (k < 5) ? cs.llr_fine + (size_t)slot * 174 : cs.saved_llr + ((size_t)slot * 5 + (k - 5)) * 174;
             apply_ap(sm.llr[wi], src, (k < 5) ? k : 0, lane);
-            found = osd_warp(sm.w[wi], sm.llr[wi], lane, S, D, bits);
+            found = osd_warp(sm.w[wi], sm.llr[wi], lane, ls, S, D, bits);
             ++n_osd;
         }
         if (lane == 0) {
@@ -281,6 +296,7 @@ __global__ void k_osd_resolve(CandState cs, const int32_t* __restrict__ list, co
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_llr_batch(const float* __restrict__ payload_db, int N, float* __restrict__ llr, float* __restrict__ sd, int32_t* __restrict__ snr) {
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const LaneSyn ls = load_lane_syn(lane);
     for (int n = blockIdx.x * WARPS_PER_CTA + wi; n < N; n += gridDim.x * WARPS_PER_CTA) {
         float p[2][8];
         if (lane < 29) {
@@ -303,13 +319,14 @@ k_ldpc_batch(float* __restrict__ llr, int N, int max_ncheck0, int max_iters, int
     load_ldpc_tables(sm.tab);
     __syncthreads();
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const LaneSyn ls = load_lane_syn(lane);
     LdpcWarpScratch& ws = sm.w[wi];
     for (int n = blockIdx.x * WARPS_PER_CTA + wi; n < N; n += gridDim.x * WARPS_PER_CTA) {
         for (int i = lane; i < 174; i += 32) ws.llr[i] = llr[(size_t)n * 174 + i];
         __syncwarp();
         uint32_t bits[3];
         int nits, iters = 0;
-        const int st = ldpc_warp(ws, sm.tab, lane, max_ncheck0, max_iters, nits, bits, iters);
+        const int st = ldpc_warp(ws, sm.tab, lane, ls, max_ncheck0, max_iters, nits, bits, iters);
         __syncwarp();
         for (int i = lane; i < 174; i += 32) llr[(size_t)n * 174 + i] = ws.llr[i];
         if (lane == 0) {
@@ -325,11 +342,12 @@ k_osd_batch(const float* __restrict__ llr, int N, int S, int D, int32_t* __restr
     extern __shared__ __align__(16) unsigned char pass_smem_raw[];
     OsdSmem& sm = *reinterpret_cast<OsdSmem*>(pass_smem_raw);
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const LaneSyn ls = load_lane_syn(lane);
     for (int n = blockIdx.x * WARPS_PER_CTA + wi; n < N; n += gridDim.x * WARPS_PER_CTA) {
         for (int i = lane; i < 174; i += 32) sm.llr[wi][i] = llr[(size_t)n * 174 + i];
         __syncwarp();
         uint32_t bits[3];
-        const int f = osd_warp(sm.w[wi], sm.llr[wi], lane, S, D, bits);
+        const int f = osd_warp(sm.w[wi], sm.llr[wi], lane, ls, S, D, bits);
         if (lane == 0) { found[n] = f; bits_out[3 * n] = bits[0]; bits_out[3 * n + 1] = bits[1]; bits_out[3 * n + 2] = bits[2]; }
         __syncwarp();
     }
