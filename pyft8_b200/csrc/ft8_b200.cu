@@ -32,6 +32,8 @@ struct ft8_handle {
     int device = 0;
     int n_sm = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;     // host->device audio copies, overlapped with S1/S2/F1 of earlier chunks
+    cudaEvent_t chunk_ev[16] = {};
     ft8_cfg cfg{};
     std::string err;
     // constant-like tables in global memory
@@ -232,7 +234,9 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
     CKC(cudaGetDeviceProperties(&prop, device));
     h->n_sm = prop.multiProcessorCount;
     CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (auto& ev : h->ev) CKC(cudaEventCreate(&ev));
+    for (auto& ev : h->chunk_ev) CKC(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CKC(upload_constant_tables());
     {
         std::vector<float> w(NFFT_S);
@@ -301,6 +305,8 @@ extern "C" void ft8_destroy(ft8_handle* h) {
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->chunk_ev) if (ev) cudaEventDestroy(ev);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -349,12 +355,15 @@ static int launch_spectrogram(ft8_handle* h, const void* d_audio, int dtype, int
     return FT8_OK;
 }
 
-static int launch_sync(ft8_handle* h, const float* d_grid, int grid_rows, int B, int odd_even) {
+// d_grid points at the first of the B cycles; b0 = index of that cycle in the handle's per-cycle arrays
+static int launch_sync(ft8_handle* h, const float* d_grid, int grid_rows, int B, int odd_even, int b0 = 0) {
     const int cycle_h0 = odd_even ? 375 : 0;
-    k_sync_scores<<<dim3(N_F0 / SY_TF, B), SY_NT, SY_SMEM_BYTES, h->stream>>>(d_grid, grid_rows, cycle_h0, h->d_best_score, h->d_best_h0);
+    const size_t K = h->cfg.max_cands;
+    k_sync_scores<<<dim3(N_F0 / SY_TF, B), SY_NT, SY_SMEM_BYTES, h->stream>>>(d_grid, grid_rows, cycle_h0, h->d_best_score + (size_t)b0 * N_F0,
+                                                                              h->d_best_h0 + (size_t)b0 * N_F0);
     CK(cudaGetLastError());
-    k_topk<<<B, 960, 0, h->stream>>>(h->d_best_score, h->d_best_h0, h->cfg.sync_score_min, h->cfg.max_cands, h->d_f0, h->d_h0,
-                                     h->d_score, h->d_ncand);
+    k_topk<<<B, 960, 0, h->stream>>>(h->d_best_score + (size_t)b0 * N_F0, h->d_best_h0 + (size_t)b0 * N_F0, h->cfg.sync_score_min,
+                                     h->cfg.max_cands, h->d_f0 + b0 * K, h->d_h0 + b0 * K, h->d_score + b0 * K, h->d_ncand + b0);
     CK(cudaGetLastError());
     return FT8_OK;
 }
@@ -662,22 +671,54 @@ extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dty
     if ((size_t)B > h->cap_cycles) return fail(h, FT8_E_CAPACITY, "ft8_decode_cycles: B exceeds cfg.max_cycles");
     const int K = h->cfg.max_cands, N = B * K;
     const int cycle_h0 = odd_even ? 375 : 0;
-    const void* da;
-    TRY(stage_audio(h, audio, audio_dtype, B, mem, &da));
+    if (audio_dtype != FT8_AUDIO_I16 && audio_dtype != FT8_AUDIO_F32) return fail(h, FT8_E_BADARG, "audio_dtype must be FT8_AUDIO_I16 or FT8_AUDIO_F32");
+    const size_t esz = audio_dtype == FT8_AUDIO_I16 ? 2 : 4;
+    const void* da = audio;
+    if (mem == FT8_MEM_HOST) { TRY(ensure_audio(h, (size_t)B * CYCLE_SAMPLES * esz)); da = h->d_audio; }
     int launches = 0;
     CK(cudaMemsetAsync(h->d_counts, 0, 8 * sizeof(int32_t), h->stream));   // [0] fine list, [1] osd list, [2] records, [4],[5] work cursors
     CK(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), h->stream));
     CK(cudaEventRecord(h->ev[0], h->stream));
-    // S1
-    TRY(launch_spectrogram(h, da, audio_dtype, B, h->d_grid)); ++launches;
-    CK(cudaEventRecord(h->ev[1], h->stream));
-    // S2
-    TRY(launch_sync(h, h->d_grid, GRID_ROWS, B, odd_even)); launches += 2;
-    CK(cudaEventRecord(h->ev[2], h->stream));
-    // F1 (independent of S1/S2; same stream)
-    TRY(launch_cycle_spectrum(h, da, audio_dtype, B, h->d_spec, FINE_SPEC_STRIDE, FINE_SPEC_STRIDE - 1));
-    launches += 2 * ((B + (int)h->y_cycles - 1) / (int)h->y_cycles);
-    CK(cudaEventRecord(h->ev[3], h->stream));
+    if (mem == FT8_MEM_HOST && B > 64) {
+        // host audio: copy in up to 16 chunks on the copy stream; S1, S2 and F1 of a chunk start as soon as it has landed,
+        // so the PCIe transfer hides behind the front-end kernels (stage timers then cover the whole front end as "S1")
+        const int nchunk = std::min(16, (B + 255) / 256);
+        const int per = (B + nchunk - 1) / nchunk;
+        CK(cudaEventRecord(h->chunk_ev[0], h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[0], 0));        // previous users of d_audio on the main stream are done
+        for (int c = 0; c < nchunk; ++c) {
+            const int b0 = c * per, nb = std::min(per, B - b0);
+            if (nb <= 0) break;
+            const size_t off = (size_t)b0 * CYCLE_SAMPLES * esz;
+            CK(cudaMemcpyAsync((char*)h->d_audio + off, (const char*)audio + off, (size_t)nb * CYCLE_SAMPLES * esz, cudaMemcpyHostToDevice, h->copy_stream));
+            CK(cudaEventRecord(h->chunk_ev[c], h->copy_stream));
+        }
+        for (int c = 0; c < nchunk; ++c) {
+            const int b0 = c * per, nb = std::min(per, B - b0);
+            if (nb <= 0) break;
+            const char* a = (const char*)h->d_audio + (size_t)b0 * CYCLE_SAMPLES * esz;
+            CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
+            TRY(launch_spectrogram(h, a, audio_dtype, nb, h->d_grid + (size_t)b0 * GRID_ROWS * GRID_COLS)); ++launches;
+            TRY(launch_sync(h, h->d_grid + (size_t)b0 * GRID_ROWS * GRID_COLS, GRID_ROWS, nb, odd_even, b0)); launches += 2;
+            TRY(launch_cycle_spectrum(h, a, audio_dtype, nb, h->d_spec + (size_t)b0 * FINE_SPEC_STRIDE, FINE_SPEC_STRIDE, FINE_SPEC_STRIDE - 1));
+            launches += 2 * ((nb + (int)h->y_cycles - 1) / (int)h->y_cycles);
+        }
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        CK(cudaEventRecord(h->ev[2], h->stream));
+        CK(cudaEventRecord(h->ev[3], h->stream));
+    } else {
+        if (mem == FT8_MEM_HOST) TRY(to_device(h, h->d_audio, audio, (size_t)B * CYCLE_SAMPLES * esz, mem));
+        // S1
+        TRY(launch_spectrogram(h, da, audio_dtype, B, h->d_grid)); ++launches;
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        // S2
+        TRY(launch_sync(h, h->d_grid, GRID_ROWS, B, odd_even)); launches += 2;
+        CK(cudaEventRecord(h->ev[2], h->stream));
+        // F1 (independent of S1/S2; same stream)
+        TRY(launch_cycle_spectrum(h, da, audio_dtype, B, h->d_spec, FINE_SPEC_STRIDE, FINE_SPEC_STRIDE - 1));
+        launches += 2 * ((B + (int)h->y_cycles - 1) / (int)h->y_cycles);
+        CK(cudaEventRecord(h->ev[3], h->stream));
+    }
     CandState cs = cand_state(h);
     // ipass 0
     k_pass0<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
