@@ -20,7 +20,6 @@ constexpr int SY_W = SY_TF + 14;          // staged columns (13 extra + 1 pad)
 constexpr int SY_ROWS = 148;              // grid rows h0+148+4k for h0 in [-37,87), k < 7 -> 111..258
 constexpr int SY_NT = 256;
 constexpr int LIVE_ROWS = 750;
-constexpr int SY_SMEM_BYTES = SY_ROWS * (SY_W + SY_TF + 2) * 4 + 8 * SY_TF * 4;
 
 __constant__ int c_costas[7] = {3, 1, 4, 0, 6, 5, 2};
 __constant__ uint8_t c_payload_sym[58] = {7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27,
@@ -35,47 +34,102 @@ __device__ __forceinline__ float grid_at(const float* g, int grid_rows, int row,
 }
 
 // grid: [B][grid_rows][976].  best_score/best_h0: [B][928].
+//
+// Shared-memory plan per CTA (58 f0 bins x all 124 h0):
+//   P2[r][c]  = g[r][c] + g[r][c+1]             148 x 70 (row stride 73: conflict-free for row-per-lane access)
+//   S14[r][c] = sum_{i<7} P2[r][c+2i]           148 x 58 (row stride 61), built with a sliding window along c
+// A hypothesis then costs 7 P2 reads (one per Costas symbol, at column f0 + 2*C[k]) plus a running sum
+// U = sum_k S14[r+4k][f0] that slides along h0 in steps of 4:  score = (7/6) * sum P2 - U/6.
+constexpr int SY_PW = 73, SY_SW = 61;
+constexpr int SY_SMEM_BYTES = SY_ROWS * (SY_PW + SY_SW) * 4 + 8 * SY_TF * 4;
+
 __global__ void __launch_bounds__(SY_NT)
 k_sync_scores(const float* __restrict__ grid, int grid_rows, int cycle_h0, float* __restrict__ best_score,
               int16_t* __restrict__ best_h0) {
     extern __shared__ __align__(16) unsigned char sy_smem_raw[];
-    float (*tile)[SY_W] = reinterpret_cast<float (*)[SY_W]>(sy_smem_raw);                                   // dB values
-    float (*box)[SY_TF + 2] = reinterpret_cast<float (*)[SY_TF + 2]>(sy_smem_raw + SY_ROWS * SY_W * 4);     // 14-bin box sums
-    float (*red_s)[SY_TF] = reinterpret_cast<float (*)[SY_TF]>(sy_smem_raw + SY_ROWS * (SY_W + SY_TF + 2) * 4);
-    int (*red_h)[SY_TF] = reinterpret_cast<int (*)[SY_TF]>(sy_smem_raw + SY_ROWS * (SY_W + SY_TF + 2) * 4 + 4 * SY_TF * 4);
+    float* P2 = reinterpret_cast<float*>(sy_smem_raw);
+    float* S14 = P2 + SY_ROWS * SY_PW;
+    float (*red_s)[SY_TF] = reinterpret_cast<float (*)[SY_TF]>(S14 + SY_ROWS * SY_SW);
+    int (*red_h)[SY_TF] = reinterpret_cast<int (*)[SY_TF]>(S14 + SY_ROWS * SY_SW + 4 * SY_TF);
     const int cyc = blockIdx.y;
     const int f_base = F0_LO + blockIdx.x * SY_TF;
     const float* g = grid + (size_t)cyc * grid_rows * GRID_COLS;
     const int row0 = cycle_h0 + H0_LO + 148;    // 111 for the even cycle
-    for (int i = threadIdx.x; i < SY_ROWS * SY_W; i += SY_NT) {
-        const int r = i / SY_W, c = i - r * SY_W;
-        const int col = f_base + c;
-        tile[r][c] = (col < GRID_COLS) ? grid_at(g, grid_rows, row0 + r, col) : 0.0f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- phase A: one warp per row; lanes hold columns lane, lane+32, lane+64 (71 needed), pair sums via shuffles
+    for (int r = warp; r < SY_ROWS; r += SY_NT / 32) {
+        int row = (row0 + r) % LIVE_ROWS;
+        if (row < 0) row += LIVE_ROWS;
+        const bool stored = row < grid_rows;
+        const float* gr = g + (size_t)row * GRID_COLS + f_base;
+        float v[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int c = lane + 32 * q;
+            v[q] = (c < 71 && f_base + c < GRID_COLS) ? (stored ? __ldg(gr + c) : 1.0f) : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            float nb = __shfl_down_sync(0xffffffffu, v[q], 1);
+            const float wrap = __shfl_sync(0xffffffffu, (q < 2) ? v[q + 1] : 0.0f, 0);
+            if (lane == 31) nb = wrap;
+            const int c = lane + 32 * q;
+            if (c < 70) P2[r * SY_PW + c] = v[q] + nb;
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < SY_ROWS * SY_TF; i += SY_NT) {
-        const int r = i / SY_TF, c = i - r * SY_TF;
+    // ---- phase B: S14 along each row with two interleaved sliding windows (even / odd columns)
+    for (int task = threadIdx.x; task < 2 * SY_ROWS; task += SY_NT) {
+        const int e = task / SY_ROWS, r = task - e * SY_ROWS;
+        const float* p = P2 + r * SY_PW;
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 14; ++j) s += tile[r][c + j];
-        box[r][c] = s;
+        for (int i = 0; i < 7; ++i) s += p[e + 2 * i];
+        float* o = S14 + r * SY_SW;
+        o[e] = s;
+        for (int c = e + 2; c < SY_TF; c += 2) {
+            s += p[c + 12] - p[c - 2];
+            o[c] = s;
+        }
     }
     __syncthreads();
-    const int f = threadIdx.x & 63, hg = threadIdx.x >> 6;    // 4 groups of 31 h0 values
+    // ---- phase C: thread = (f0, group of 31 h0); ascending h0, strict '>' from 0 (receiver.py:345-354)
+    const int f = threadIdx.x & 63, hg = threadIdx.x >> 6;
     float best = 0.0f;
     int best_h = 0;
     if (f < SY_TF) {
-        const float c6 = -1.0f / 6.0f;
-        for (int hh = hg * 31; hh < hg * 31 + 31; ++hh) {
-            float s = 0.f;
+        constexpr int C0 = 6, C1 = 2, C2 = 8, C3 = 0, C4 = 12, C5 = 10, C6 = 4;     // 2 * Costas tone
+        const int h_lo = hg * 31;
+        const float* pf = P2 + f;
+        const float* sf = S14 + f;
+        float U[4];
 #pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const int r = hh + 4 * k;
-                const int c = f + 2 * c_costas[k];
-                const float p2 = tile[r][c] + tile[r][c + 1];
-                s += fmaf(box[r][f] - p2, c6, p2);
+        for (int j = 0; j < 4; ++j) {
+            float u = 0.f;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) u += sf[(h_lo + j + 4 * k) * SY_SW];
+            U[j] = u;
+        }
+        const float k76 = 7.0f / 6.0f, c6 = -1.0f / 6.0f;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j;
+                if (i < 31) {
+                    const int hh = h_lo + i;
+                    const float* p = pf + hh * SY_PW;
+                    float sp = p[C0] + p[4 * SY_PW + C1];
+                    sp += p[8 * SY_PW + C2];
+                    sp += p[12 * SY_PW + C3];
+                    sp += p[16 * SY_PW + C4];
+                    sp += p[20 * SY_PW + C5];
+                    sp += p[24 * SY_PW + C6];
+                    const float sc = fmaf(sp, k76, U[j] * c6);
+                    if (sc > best) { best = sc; best_h = hh + H0_LO; }
+                    if (i + 4 < 31) U[j] += sf[(hh + 28) * SY_SW] - sf[hh * SY_SW];
+                }
             }
-            if (s > best) { best = s; best_h = hh + H0_LO; }
         }
         red_s[hg][f] = best;
         red_h[hg][f] = best_h;
