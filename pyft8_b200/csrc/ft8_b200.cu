@@ -57,7 +57,7 @@ struct ft8_handle {
     int32_t *d_list_fine = nullptr, *d_list_osd = nullptr, *d_counts = nullptr;   // counts: [0] fine, [1] osd, [2] records
     DevStats* d_stats = nullptr;
     ft8_record* d_rec = nullptr;
-    ft8_record* h_rec = nullptr;      // pinned staging
+    int32_t *d_rec_n = nullptr, *d_rec_base = nullptr;   // per-cycle record counts / offsets
     int32_t* h_counts = nullptr;      // pinned
     DevStats* h_stats = nullptr;      // pinned
     // generic arena for the stand-alone stage ops
@@ -65,7 +65,6 @@ struct ft8_handle {
     cudaEvent_t ev[12] = {};          // ev[0..8]: stage boundaries of ft8_decode_cycles; ev[10], ev[11]: stand-alone ops
     float last_ms[9] = {};            // see ft8_last_kernel_ms
     ft8_stats stats{};
-    std::vector<int32_t> host_offs, host_idx, host_cur;   // host-side ordering scratch
 };
 
 #define CK(call)                                                                                   \
@@ -272,8 +271,7 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
     CKC(dmalloc(&h->d_ripass, N)); CKC(dmalloc(&h->d_rap, N)); CKC(dmalloc(&h->d_rmethod, N)); CKC(dmalloc(&h->d_rnits, N));
     CKC(dmalloc(&h->d_osd_found, N * 10)); CKC(dmalloc(&h->d_osd_bits, N * 30));
     CKC(dmalloc(&h->d_list_fine, N)); CKC(dmalloc(&h->d_list_osd, N)); CKC(dmalloc(&h->d_counts, 8));
-    CKC(dmalloc(&h->d_stats, 1)); CKC(dmalloc(&h->d_rec, N));
-    CKC(cudaMallocHost((void**)&h->h_rec, N * sizeof(ft8_record)));
+    CKC(dmalloc(&h->d_stats, 1)); CKC(dmalloc(&h->d_rec, N)); CKC(dmalloc(&h->d_rec_n, B)); CKC(dmalloc(&h->d_rec_base, B));
     CKC(cudaMallocHost((void**)&h->h_counts, 4 * sizeof(int32_t)));
     CKC(cudaMallocHost((void**)&h->h_stats, sizeof(DevStats)));
     {
@@ -299,9 +297,8 @@ extern "C" void ft8_destroy(ft8_handle* h) {
                     h->d_pulse, h->d_audio, h->d_grid, h->d_Y, h->d_spec, h->d_best_score, h->d_best_h0, h->d_f0, h->d_h0, h->d_score,
                     h->d_ncand, h->d_cycle_of, h->d_status, h->d_llr_grid, h->d_grid_sd, h->d_grid_snr, h->d_llr_fine, h->d_fine,
                     h->d_saved, h->d_saved_n, h->d_saved_ap, h->d_bits, h->d_ripass, h->d_rap, h->d_rmethod, h->d_rnits,
-                    h->d_osd_found, h->d_osd_bits, h->d_list_fine, h->d_list_osd, h->d_counts, h->d_stats, h->d_rec, h->arena};
+                    h->d_osd_found, h->d_osd_bits, h->d_list_fine, h->d_list_osd, h->d_counts, h->d_stats, h->d_rec, h->d_rec_n, h->d_rec_base, h->arena};
     for (void* p : ptrs) if (p) cudaFree(p);
-    if (h->h_rec) cudaFreeHost(h->h_rec);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -640,19 +637,122 @@ extern "C" int ft8_crc14(ft8_handle* h, const uint32_t* bits91, int N, int32_t* 
 }
 
 // ------------------------------------------------------------------------------------------ whole path
-__global__ void k_collect(CandState cs, int n_slots, FineOut* __restrict__ fine, ft8_record* __restrict__ rec, int32_t* __restrict__ n_rec) {
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots; slot += gridDim.x * blockDim.x) {
-        const int cyc = slot / cs.K, rank = slot - cyc * cs.K;
-        if (rank >= cs.n_cand[cyc] || cs.status[slot] != ST_DECODED) continue;
+// Record packaging on the device (R1; receiver.py:51-66, 389-398).  One CTA per cycle orders that cycle's decoded
+// candidates in the reference's emission order -- pass by pass; inside a pass by llr_sd descending (the fine sd from
+// ipass 2 on, all-equal before), ties by candidate rank -- flags later duplicates of a payload (receiver.py:53-55) and
+// writes the records contiguously at base[cycle], so the host only copies.
+constexpr int REC_MAXC = 928, REC_NT = 256;
+
+__global__ void __launch_bounds__(REC_NT) k_rec_count(CandState cs, int32_t* __restrict__ n_per_cycle) {
+    __shared__ int cnt;
+    const int cyc = blockIdx.x;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const int n = cs.n_cand[cyc];
+    int c = 0;
+    for (int r = threadIdx.x; r < n; r += REC_NT) c += cs.status[cyc * cs.K + r] == ST_DECODED;
+    if (c) atomicAdd(&cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) n_per_cycle[cyc] = cnt;
+}
+
+// exclusive scan of n_per_cycle[B] -> base[B], total -> *total (single CTA)
+__global__ void __launch_bounds__(1024) k_rec_scan(const int32_t* __restrict__ n_per_cycle, int B, int32_t* __restrict__ base,
+                                                   int32_t* __restrict__ total) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < B; b0 += 1024) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < B ? n_per_cycle[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warp_sum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int s = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            warp_sum[lane] = s;
+        }
+        __syncthreads();
+        const int before = carry + (w ? warp_sum[w - 1] : 0) + x - v;
+        if (i < B) base[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(REC_NT)
+k_rec_write(CandState cs, const FineOut* __restrict__ fine, const int32_t* __restrict__ base, ft8_record* __restrict__ rec,
+            DevStats* __restrict__ stats) {
+    __shared__ uint16_t s_rank[REC_MAXC];      // candidate rank (index inside the cycle) of the i-th decoded candidate
+    __shared__ uint8_t s_ipass[REC_MAXC];
+    __shared__ float s_sd[REC_MAXC];
+    __shared__ uint32_t s_w[REC_MAXC][3];
+    __shared__ int s_n, s_emit;
+    const int cyc = blockIdx.x, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { s_n = 0; s_emit = 0; }
+    __syncthreads();
+    const int n = cs.n_cand[cyc];
+    // compaction in candidate order (ballot scan per warp-sized chunk keeps it deterministic)
+    for (int r0 = 0; r0 < n; r0 += REC_NT) {
+        const int r = r0 + threadIdx.x;
+        const bool dec = r < n && cs.status[cyc * cs.K + r] == ST_DECODED;
+        const uint32_t m = __ballot_sync(0xffffffffu, dec);
+        __shared__ int wbase[REC_NT / 32];
+        if (lane == 0) wbase[threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        int off = s_n;
+        for (int w = 0; w < (threadIdx.x >> 5); ++w) off += wbase[w];
+        if (dec) {
+            const int i = off + __popc(m & ((1u << lane) - 1u));
+            const int slot = cyc * cs.K + r;
+            s_rank[i] = (uint16_t)r;
+            s_ipass[i] = cs.r_ipass[slot];
+            s_sd[i] = cs.r_ipass[slot] >= 2 ? fine[slot].sd : 0.0f;
+            s_w[i][0] = cs.bits91[3 * slot]; s_w[i][1] = cs.bits91[3 * slot + 1]; s_w[i][2] = cs.bits91[3 * slot + 2] & 0x1FFFu;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < REC_NT / 32; ++w) t += wbase[w]; s_n += t; }
+        __syncthreads();
+    }
+    const int nd = s_n;
+    int emitted_here = 0;
+    for (int i = threadIdx.x; i < nd; i += REC_NT) {
+        const int ip = s_ipass[i];
+        const float sd = s_sd[i];
+        const int rk = s_rank[i];
+        int pos = 0;
+        bool dup = false;
+        for (int j = 0; j < nd; ++j) {
+            const int jp = s_ipass[j];
+            bool before;                      // does j precede i in emission order?
+            if (jp != ip) before = jp < ip;
+            else if (ip >= 2 && s_sd[j] != sd) before = s_sd[j] > sd;
+            else before = s_rank[j] < rk;
+            if (before) {
+                ++pos;
+                dup = dup || (s_w[j][0] == s_w[i][0] && s_w[j][1] == s_w[i][1] && s_w[j][2] == s_w[i][2]);
+            }
+        }
+        const int slot = cyc * cs.K + rk;
         ft8_record r;
         memset(&r, 0, sizeof(r));
         r.bits91[0] = cs.bits91[3 * slot]; r.bits91[1] = cs.bits91[3 * slot + 1]; r.bits91[2] = cs.bits91[3 * slot + 2];
-        r.cycle = cyc; r.cand = (int16_t)rank; r.f0_idx = cs.f0[slot]; r.h0_idx = cs.h0[slot];
-        r.ipass = cs.r_ipass[slot]; r.ap = cs.r_ap[slot]; r.method = cs.r_method[slot]; r.n_its = cs.r_nits[slot];
+        r.cycle = cyc; r.cand = (int16_t)rk; r.f0_idx = cs.f0[slot]; r.h0_idx = cs.h0[slot];
+        r.ipass = (uint8_t)ip; r.ap = cs.r_ap[slot]; r.method = cs.r_method[slot]; r.n_its = cs.r_nits[slot];
         r.score = cs.score[slot]; r.grid_sd = cs.grid_sd[slot];
+        r.emitted = dup ? 0 : 1;
+        emitted_here += dup ? 0 : 1;
         // float(h0/25) and 3.125*f0 like receiver.py:350-351 (python floats; rounded to fp32 for the record)
         double tsec = (double)r.h0_idx / 25.0, fhz = 3.125 * (double)r.f0_idx;
-        if (r.ipass >= 2) {
+        if (ip >= 2) {
             const FineOut fo = fine[slot];
             r.ttweak = (int8_t)fo.tt; r.ftweak = (int8_t)fo.ff; r.nsync = (uint8_t)fo.nsync; r.fine_sd = fo.sd; r.snr = (int8_t)fo.snr;
             tsec += (double)fo.tt / 200.0; fhz += (double)fo.ff / 16.0;
@@ -660,8 +760,11 @@ __global__ void k_collect(CandState cs, int n_slots, FineOut* __restrict__ fine,
             r.nsync = 100; r.fine_sd = nanf(""); r.snr = cs.grid_snr[slot];
         }
         r.tsec = (float)tsec; r.fHz = (float)fhz;
-        rec[atomicAdd(n_rec, 1)] = r;
+        rec[base[cyc] + pos] = r;
     }
+    if (emitted_here) atomicAdd(&s_emit, emitted_here);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_emit) atomicAdd(&stats->emitted, (unsigned long long)s_emit);
 }
 
 extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even, ft8_record* rec,
@@ -743,67 +846,31 @@ extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dty
     k_osd_resolve<<<persistent_blocks(h, 2), 128, 0, h->stream>>>(cs, h->d_list_osd, h->d_counts + 1, h->d_stats);
     CK(cudaGetLastError()); ++launches;
     CK(cudaEventRecord(h->ev[7], h->stream));
-    k_collect<<<persistent_blocks(h, 4), 256, 0, h->stream>>>(cs, N, h->d_fine, h->d_rec, h->d_counts + 2);
+    k_rec_count<<<B, REC_NT, 0, h->stream>>>(cs, h->d_rec_n);
+    CK(cudaGetLastError()); ++launches;
+    k_rec_scan<<<1, 1024, 0, h->stream>>>(h->d_rec_n, B, h->d_rec_base, h->d_counts + 2);
+    CK(cudaGetLastError()); ++launches;
+    k_rec_write<<<B, REC_NT, 0, h->stream>>>(cs, h->d_fine, h->d_rec_base, h->d_rec, h->d_stats);
     CK(cudaGetLastError()); ++launches;
     CK(cudaEventRecord(h->ev[8], h->stream));
     CK(cudaMemcpyAsync(h->h_counts, h->d_counts, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(n_rec, h->d_rec_n, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     const int nrec = h->h_counts[2];
-    if (nrec > 0) {
-        CK(cudaMemcpyAsync(h->h_rec, h->d_rec, (size_t)nrec * sizeof(ft8_record), cudaMemcpyDeviceToHost, h->stream));
+    const int ncopy = std::min(nrec, rec_capacity);
+    if (ncopy > 0) {
+        CK(cudaMemcpyAsync(rec, h->d_rec, (size_t)ncopy * sizeof(ft8_record), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    const bool overflow = nrec > rec_capacity;
+    if (overflow) {                       // records are cycle-major: trim the per-cycle counts to what was copied
+        int left = rec_capacity;
+        for (int b = 0; b < B; ++b) { const int t = std::min(n_rec[b], left); n_rec[b] = t; left -= t; }
+    }
+    const int64_t emitted = (int64_t)h->h_stats->emitted;
     CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[8]));
     for (int i = 1; i <= 8; ++i) CK(cudaEventElapsedTime(&h->last_ms[i], h->ev[i - 1], h->ev[i]));
-    // emission order (receiver.py:389-398): pass by pass; inside a pass by llr_sd descending (the fine sd from
-    // ipass 2 on, all-equal before), ties by candidate rank; then de-dup on the payload (receiver.py:53-55).
-    // Records arrive in atomic-append order: bucket by cycle (counting sort), then order each cycle's few dozen records.
-    std::vector<int32_t>& offs = h->host_offs;
-    std::vector<int32_t>& idx = h->host_idx;
-    offs.assign((size_t)B + 1, 0);
-    idx.resize((size_t)std::max(nrec, 1));
-    for (int i = 0; i < nrec; ++i) offs[h->h_rec[i].cycle + 1]++;
-    for (int b = 0; b < B; ++b) offs[b + 1] += offs[b];
-    {
-        std::vector<int32_t>& cur = h->host_cur;
-        cur.assign(offs.begin(), offs.end() - 1);
-        for (int i = 0; i < nrec; ++i) idx[cur[h->h_rec[i].cycle]++] = i;
-    }
-    const ft8_record* R = h->h_rec;
-    int64_t emitted = 0;
-    int written = 0;
-    bool overflow = false;
-    constexpr int HT = 1024;                       // per-cycle open-addressed set of payloads (<= 928 records per cycle)
-    int32_t ht[HT];
-    for (int b = 0; b < B; ++b) {
-        n_rec[b] = 0;
-        int32_t* lo = idx.data() + offs[b];
-        int32_t* hi = idx.data() + offs[b + 1];
-        if (lo == hi) continue;
-        std::sort(lo, hi, [R](int32_t x, int32_t y) {
-            const ft8_record &a = R[x], &c = R[y];
-            if (a.ipass != c.ipass) return a.ipass < c.ipass;
-            if (a.ipass >= 2 && a.fine_sd != c.fine_sd) return a.fine_sd > c.fine_sd;
-            return a.cand < c.cand;
-        });
-        for (int i = 0; i < HT; ++i) ht[i] = -1;
-        for (int32_t* it = lo; it != hi; ++it) {
-            ft8_record r = R[*it];
-            const uint32_t w2 = r.bits91[2] & 0x1FFFu;           // payload = bits 0..76
-            uint32_t hsh = (r.bits91[0] * 0x9E3779B1u) ^ (r.bits91[1] * 0x85EBCA77u) ^ (w2 * 0xC2B2AE3Du);
-            hsh = (hsh ^ (hsh >> 15)) & (HT - 1);
-            r.emitted = 1;
-            while (ht[hsh] >= 0) {
-                const ft8_record& q = R[ht[hsh]];
-                if (q.bits91[0] == r.bits91[0] && q.bits91[1] == r.bits91[1] && (q.bits91[2] & 0x1FFFu) == w2) { r.emitted = 0; break; }
-                hsh = (hsh + 1) & (HT - 1);
-            }
-            if (r.emitted) ht[hsh] = *it;
-            emitted += r.emitted;
-            if (written < rec_capacity) { rec[written++] = r; n_rec[b]++; } else overflow = true;
-        }
-    }
     ft8_stats& s = h->stats;
     memset(&s, 0, sizeof(s));
     s.cycles = B; s.candidates = (int64_t)h->h_stats->candidates; s.stopped_sd = (int64_t)h->h_stats->stopped_sd;

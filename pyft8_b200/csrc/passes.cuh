@@ -67,7 +67,7 @@ struct CandState {            // structure-of-arrays views over all B*K slots
 };
 
 struct DevStats {
-    unsigned long long candidates, stopped_sd, fine_evals, fine_pass, ldpc_calls, ldpc_iters, osd_calls, decoded;
+    unsigned long long candidates, stopped_sd, fine_evals, fine_pass, ldpc_calls, ldpc_iters, osd_calls, decoded, emitted;
 };
 
 struct PassSmem {
