@@ -363,3 +363,26 @@ def test_device_generator_decodes_like_host_generator(eng):
     rec, _ = eng.decode_cycles(a)
     got = {bits91_to_int(r["bits91"]) >> 14 for r in rec}
     assert len(got & set(b77)) >= 9
+
+
+def test_parity_sweep_device_generated_batch(eng):
+    """A batch of BASELINE-config-2 cycles made by the generator kernel: emitted payload sets equal the oracle's per cycle."""
+    import torch
+    from pyft8_b200 import workload
+    n = 6
+    params = workload.make_params("cfg2_50sig", n, seed=77)
+    audio = torch.empty((n, 180000), dtype=torch.int16, device="cuda:0")
+    workload.device_cycles(eng, params, audio.data_ptr())
+    torch.cuda.synchronize()
+    host = audio.cpu().numpy()
+    rec, cnt = eng.decode_cycles(host)
+    rec_d, cnt_d = eng.decode_cycles_dev(audio.data_ptr(), L.AUDIO_I16, n)        # device-resident input gives the same
+    assert np.array_equal(cnt, cnt_d) and np.array_equal(rec["bits91"], rec_d["bits91"])
+    off = 0
+    for b in range(n):
+        r = rec[off:off + cnt[b]]
+        off += cnt[b]
+        got = [bits91_to_int(x["bits91"]) >> 14 for x in r[r["emitted"] == 1]]
+        want = [x["bits77"] for x in o.decode_cycle(host[b])[0]]
+        assert set(got) == set(want), b
+        assert len(got) == len(set(got))
