@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libft8_b200.so")
+LIB_PATH = os.environ.get("PYFT8_B200_LIB") or os.path.join(_HERE, "libft8_b200.so")   # env override: A/B builds
 
 OK, E_BADARG, E_CUDA, E_CAPACITY, E_NODEVICE = 0, -1, -2, -3, -4
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -27,6 +27,9 @@ namespace ft8 {
 constexpr int CS_N = 96000, CS_N1 = 375, CS_N2 = 256, CS_COLS = 16, CS_NT = 256;
 constexpr int FINE_SPEC_STRIDE = 49152;
 constexpr int FINE_N = 3200, FINE_NT = 256;
+#ifndef FINE_BUFS
+#define FINE_BUFS 3        // 3: ping-pong passes, 2 CTAs/SM; 2: in-place middle passes, 3 CTAs/SM
+#endif
 
 template <typename T> __device__ __forceinline__ float2 load_pair(const T* x, int n);
 template <> __device__ __forceinline__ float2 load_pair<int16_t>(const int16_t* x, int n) {
@@ -158,9 +161,17 @@ __device__ __forceinline__ void fine_ifft(float2* dst, float2* tmp, const float2
         }
     }
     __syncthreads();
+#if FINE_BUFS == 3
     pass_oop<3200, 5, 5, FINE_NT, true>(tmp, dst, tid, W3200);
     pass_oop<3200, 8, 25, FINE_NT, true>(dst, tmp, tid, W3200);
     pass_oop<3200, 16, 200, FINE_NT, true>(tmp, dst, tid, W3200);
+#else
+    // two-buffer variant: tmp == dst; middle passes are staged through registers (read all, barrier, write, barrier),
+    // the last pass (M = 1) is naturally in place: every thread reads and writes the same 16 positions
+    pass_inplace<3200, 5, 5, FINE_NT, true>(dst, tid, W3200, CtaSync());
+    pass_inplace<3200, 8, 25, FINE_NT, true>(dst, tid, W3200, CtaSync());
+    pass_oop<3200, 16, 200, FINE_NT, true>(dst, dst, tid, W3200);
+#endif
 }
 
 // 32-sample symbol DFT by one warp (receiver.py:195): lane m holds z[i0+m] and its twiddles tw[t] = exp(-2 pi i t m/32),
@@ -213,19 +224,18 @@ __device__ __forceinline__ float costas_row(const float2* z, int tb, int k, int 
     return c;                                           // lanes with (lane & 3) == 0 hold the total
 }
 
-constexpr int FINE_SMEM_BYTES = 3 * FINE_N * (int)sizeof(float2) + (79 * 8 + 8 * 49 + 16 + 100) * (int)sizeof(float) + 32 * (int)sizeof(float2);
+constexpr int FINE_SMEM_BYTES = FINE_BUFS * FINE_N * (int)sizeof(float2) + (79 * 8 + 16 + 100) * (int)sizeof(float) + 32 * (int)sizeof(float2);
 
 // One CTA per work item (grid-stride over list[0..*count)).  cand arrays are indexed by the global slot id.
 // spec: [B][spec_stride] float2.  Outputs per slot: fo[slot], llr_fine[slot][174], optional sig_grid[slot][79][8].
-__global__ void __launch_bounds__(FINE_NT, 2)
+__global__ void __launch_bounds__(FINE_NT, FINE_BUFS == 3 ? 2 : 3)
 k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restrict__ list, const int32_t* __restrict__ count,
        int n_direct, const int32_t* __restrict__ cycle_of, const int16_t* __restrict__ cand_f0,
        const int16_t* __restrict__ cand_h0, const float2* __restrict__ W3200, FineOut* __restrict__ fo,
        float* __restrict__ llr_fine, float* __restrict__ sig_grid) {
     extern __shared__ float2 fine_smem[];
-    float* G = reinterpret_cast<float*>(fine_smem + 3 * FINE_N);      // [79][8]
-    float* g49 = G + 79 * 8;                                          // [8][49]
-    float* score = g49 + 8 * 49;                                      // [16]
+    float* G = reinterpret_cast<float*>(fine_smem + FINE_BUFS * FINE_N);      // [79][8]
+    float* score = G + 79 * 8;                                        // [16]
     float* taper = score + 16;                                        // [100]
     float2* w32 = reinterpret_cast<float2*>(taper + 100);             // [32]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -244,7 +254,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         const int fb0 = 50 * f0;                                   // int(0.5 + 16*fHz), fHz = 3.125*f0
         const int tb0 = (h0 >= 0) ? 8 * h0 : 8 * h0 + 1;           // int(0.5 + 200*tsec) truncates toward zero
         // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT; warp w scores start w
-        fine_ifft(fine_smem, fine_smem + FINE_N, sp, fb0, tid, W3200, taper);
+        fine_ifft(fine_smem, FINE_BUFS == 3 ? fine_smem + FINE_N : fine_smem, sp, fb0, tid, W3200, taper);
         {
             float sc = 0.0f;
 #pragma unroll 1
@@ -265,7 +275,11 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         float bestf = 0.0f;
         for (int q = -1; q < 8; ++q) {
             const int fi = q < 0 ? 4 : (q < 4 ? q : q + 1);
+#if FINE_BUFS == 3
             const int cur = q < 0 ? 0 : (keep + 1) % 3, scratch = (keep + 2) % 3;   // the three buffers rotate around the best
+#else
+            const int cur = q < 0 ? 0 : keep ^ 1, scratch = cur;                     // best in one buffer, work in the other
+#endif
             if (q >= 0) fine_ifft(fine_smem + cur * FINE_N, fine_smem + scratch * FINE_N, sp, fb0 + (-32 + 8 * fi), tid, W3200, taper);
             if (warp < 7) {
                 const float r = costas_row(fine_smem + cur * FINE_N, tb0 + tt, warp, lane, tw);

@@ -21,8 +21,12 @@ constexpr int SP_ROWS = 4;          // rows per CTA
 constexpr int SP_NT = 128;          // threads per row
 constexpr int GRID_ROWS = 376, GRID_COLS = 976, CYCLE_SAMPLES = 180000, NFFT_S = 3840, HOP = 480;
 
-__device__ __forceinline__ float load_sample(const int16_t* a, int i) { return (float)a[i]; }
-__device__ __forceinline__ float load_sample(const float* a, int i) { return a[i]; }
+// two consecutive samples starting at an even index (one 32-bit / 64-bit load)
+__device__ __forceinline__ float2 load_sample_pair(const int16_t* a, int i) {
+    const short2 v = __ldg(reinterpret_cast<const short2*>(a + i));
+    return make_float2((float)v.x, (float)v.y);
+}
+__device__ __forceinline__ float2 load_sample_pair(const float* a, int i) { return __ldg(reinterpret_cast<const float2*>(a + i)); }
 
 template <typename T>
 __global__ void __launch_bounds__(SP_ROWS* SP_NT)
@@ -53,13 +57,13 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
             for (int j = 0; j < 3; ++j) {
                 const int n = p + 640 * j;
                 const int si = s0 + 2 * n;
-                float re = 0.f, im = 0.f;
-                if (live && si >= 0) {
-                    const float2 w = *reinterpret_cast<const float2*>(hann + 2 * n);
-                    re = load_sample(x, si) * w.x;
-                    im = load_sample(x, si + 1) * w.y;
+                float2 z = make_float2(0.f, 0.f);
+                if (live && si >= 0) {                      // si is even: the pair never straddles the cycle start
+                    const float2 w = __ldg(reinterpret_cast<const float2*>(hann + 2 * n));
+                    const float2 v = load_sample_pair(x, si);
+                    z = make_float2(v.x * w.x, v.y * w.y);
                 }
-                a[i][j] = make_float2(re, im);
+                a[i][j] = z;
             }
         }
 #pragma unroll
@@ -68,7 +72,7 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
     }
     pass_inplace<1920, 5, 3, SP_NT, false>(buf, lt, W1920, CtaSync());
     pass_inplace<1920, 8, 15, SP_NT, false>(buf, lt, W1920, CtaSync());
-    pass_inplace<1920, 16, 120, SP_NT, false>(buf, lt, W1920, CtaSync());
+    pass_oop<1920, 16, 120, SP_NT, false>(buf, buf, lt, W1920);   // last pass (M = 1): each thread rewrites the 16 positions it read
 
     // untangle the real transform for bins 0..975 and write dB
     if (live) {
@@ -80,8 +84,10 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
             const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));   // -i/2 * (zk - conj(zm))
             const float2 w = __ldg(&W3840[k]);
             const float2 X = cadd(e, cmul(o, w));
-            const float mag = sqrtf(fmaf(X.x, X.x, X.y * X.y));
-            row[k] = 20.0f * log10f(mag + 1e-12f);
+            // 20*log10(|X| + 1e-12): for |X|^2 > 1e-8 the 1e-12 is below half an ulp of |X| and 20*log10|X| = 10*log10(|X|^2),
+            // evaluated as (10*log10(2)) * log2 with the 2-ulp hardware log2; the exact form is kept for (near-)silent bins
+            const float pw = fmaf(X.x, X.x, X.y * X.y);
+            row[k] = (pw > 1e-8f) ? 3.01029995663981195f * __log2f(pw) : 20.0f * log10f(sqrtf(pw) + 1e-12f);
         }
     }
 }
