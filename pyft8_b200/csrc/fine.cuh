@@ -48,10 +48,24 @@ k_cs_cols(const T* __restrict__ audio, float2* __restrict__ Y, const float2* __r
     extern __shared__ float2 cs_smem[];          // [16][375]
     const int cyc = blockIdx.y, n2_0 = blockIdx.x * CS_COLS;
     const T* x = audio + (size_t)cyc * CYCLE_SAMPLES;
-    for (int i = threadIdx.x; i < CS_COLS * CS_N1; i += CS_NT) {
-        const int n1 = i / CS_COLS, c = i - n1 * CS_COLS;
-        const int n = CS_N2 * n1 + n2_0 + c;
-        cs_smem[c * CS_N1 + n1] = (n < CYCLE_SAMPLES / 2) ? load_pair<T>(x, n) : make_float2(0.f, 0.f);
+    // 6000 sample pairs per CTA: batches of 8 independent loads per thread keep the memory pipe busy
+    constexpr int LD_ITERS = (CS_COLS * CS_N1 + CS_NT - 1) / CS_NT;      // 24
+#pragma unroll
+    for (int b0 = 0; b0 < LD_ITERS; b0 += 8) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = threadIdx.x + (b0 + u) * CS_NT;
+            const int n1 = i / CS_COLS, c = i - n1 * CS_COLS;
+            const int n = CS_N2 * n1 + n2_0 + c;
+            v[u] = (i < CS_COLS * CS_N1 && n < CYCLE_SAMPLES / 2) ? load_pair<T>(x, n) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = threadIdx.x + (b0 + u) * CS_NT;
+            const int n1 = i / CS_COLS, c = i - n1 * CS_COLS;
+            if (i < CS_COLS * CS_N1) cs_smem[c * CS_N1 + n1] = v[u];
+        }
     }
     __syncthreads();
     pass_inplace_batched<375, 3, 1, CS_COLS, CS_NT, false>(cs_smem, threadIdx.x, W375);
@@ -75,15 +89,16 @@ k_cs_rows(const float2* __restrict__ Y, float2* __restrict__ spec, int spec_stri
     __shared__ float2 rows[2 * CSR_G][CS_N2];     // [0..7] rows k1, [8..15] mirror rows 375-k1
     const int cyc = blockIdx.y, g0 = blockIdx.x * CSR_G;
     const float2* y = Y + (size_t)cyc * CS_N;
-    for (int i = threadIdx.x; i < 2 * CSR_G * CS_N2; i += CS_NT) {
-        const int r = i / CS_N2, c = i - r * CS_N2;
-        const int k1 = g0 + (r & (CSR_G - 1));
-        float2 v = make_float2(0.f, 0.f);
-        if (k1 <= 187) {
+    {
+        float2 v[2 * CSR_G];                         // thread = column; 16 independent row loads in flight
+#pragma unroll
+        for (int r = 0; r < 2 * CSR_G; ++r) {
+            const int k1 = g0 + (r & (CSR_G - 1));
             const int row = (r < CSR_G) ? k1 : (CS_N1 - k1) % CS_N1;
-            v = y[row * CS_N2 + c];
+            v[r] = (k1 <= 187) ? y[row * CS_N2 + threadIdx.x] : make_float2(0.f, 0.f);
         }
-        rows[r][c] = v;
+#pragma unroll
+        for (int r = 0; r < 2 * CSR_G; ++r) rows[r][threadIdx.x] = v[r];
     }
     __syncthreads();
     pass_inplace_batched<256, 16, 1, 2 * CSR_G, CS_NT, false>(&rows[0][0], threadIdx.x, W256);
