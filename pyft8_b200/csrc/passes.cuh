@@ -31,6 +31,7 @@ __constant__ ApTables c_ap;
 
 // Candidate._set_AP (receiver.py:109-117): dst = src with known bits forced to +-5
 __device__ __forceinline__ void apply_ap(float* dst, const float* src, int ap, int lane) {
+    __syncwarp();                 // earlier reads of dst by other lanes (previous attempt) are complete
     for (int i = lane; i < 174; i += 32) dst[i] = src[i];
     __syncwarp();
     if (ap > 0) {
