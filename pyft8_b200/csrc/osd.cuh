@@ -31,8 +31,6 @@ __constant__ OsdTables c_osd;
 constexpr int OSD_MAX_FLIPS = 91;
 
 struct OsdWarpScratch {
-    unsigned long long key[176];     // sort keys
-    uint8_t perm[192];               // sorted position -> original column
     uint8_t piv_row[96];             // pivot k -> row
     uint32_t vec[OSD_MAX_FLIPS + 1][4];   // [0] = order-0 word, [1+i] = row of T for flip i; [..][3] = CRC syndrome
 };
@@ -40,34 +38,52 @@ struct OsdWarpScratch {
 // Returns trial index + 1 of the first accepted trial word (0 = none); bits = that word.
 // llr: 174 floats in shared or global memory.
 __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int lane, const LaneSyn& ls, int S, int D, uint32_t* bits) {
-    // ---- 1. reliability order by rank counting
-    for (int i = lane; i < 174; i += 32) {
-        const float a = fabsf(llr[i]);
-        const uint32_t u = (a != a) ? 0u : (__float_as_uint(a) + 1u);       // NaN sorts last
-        s.key[i] = ((unsigned long long)u << 8) | (unsigned long long)(255 - i);
+    // ---- 1. reliability order: bitonic sort of 256 64-bit keys (8 per lane, slot e = 32*r + lane), descending.
+    //      key = (|llr| bits + 1, or 0 for NaN) << 8 | (255 - index): larger |llr| first, ties by ascending index, NaN after
+    //      every number, the 82 padding slots (key 0) last.  Slot e ends up holding the e-th column in reliability order.
+    unsigned long long key[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = 32 * r + lane;
+        unsigned long long k = 0ull;
+        if (i < 174) {
+            const float a = fabsf(llr[i]);
+            const uint32_t u = (a != a) ? 0u : (__float_as_uint(a) + 1u);
+            k = ((unsigned long long)u << 8) | (unsigned long long)(255 - i);
+        }
+        key[r] = k;
     }
-    __syncwarp();
-    {
-        unsigned long long mine[6];
-        int rank[6];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const int i = lane + 32 * r;
-            mine[r] = (i < 174) ? s.key[i] : 0ull;
-            rank[r] = 0;
-        }
-        for (int j = 0; j < 174; ++j) {
-            const unsigned long long k = s.key[j];
+    for (int k = 2; k <= 256; k <<= 1) {
 #pragma unroll
-            for (int r = 0; r < 6; ++r) rank[r] += (k > mine[r]) ? 1 : 0;
-        }
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {                                   // partner slot lives in the same lane
+                const int jr = j >> 5;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const int i = lane + 32 * r;
-            if (i < 174) s.perm[rank[r]] = (uint8_t)i;
+                for (int r = 0; r < 8; ++r) {
+                    if ((r & jr) == 0) {
+                        const int e = 32 * r;                // lane bits do not matter for k >= 64
+                        const bool desc = (e & k) == 0;
+                        const unsigned long long x = key[r], y = key[r | jr];
+                        const bool sw = desc ? (x < y) : (x > y);
+                        key[r] = sw ? y : x;
+                        key[r | jr] = sw ? x : y;
+                    }
+                }
+            } else {                                         // partner slot is in lane ^ j, same register
+                const bool lower = (lane & j) == 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int e = 32 * r + lane;
+                    const bool desc = (e & k) == 0;
+                    const unsigned long long x = key[r];
+                    const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, j);
+                    const bool take_max = (lower == desc);
+                    key[r] = (take_max == (x > y)) ? x : y;
+                }
+            }
         }
     }
-    __syncwarp();
     // ---- 2. load columns in sorted order; hard decisions per sorted position
     uint32_t c0[6], c1[6], c2[6];
     uint32_t hard_mask = 0;          // bit r: hard decision of this lane's slot r
@@ -76,7 +92,7 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int
     for (int r = 0; r < 6; ++r) {
         const int sp = lane + 32 * r;
         if (sp < 174) {
-            const int c = s.perm[sp];
+            const int c = 255 - (int)(key[r] & 0xFFull);
             orig[r] = c;
             c0[r] = c_osd.col[c][0]; c1[r] = c_osd.col[c][1]; c2[r] = c_osd.col[c][2];
             if (llr[c] > 0.0f) hard_mask |= 1u << r;

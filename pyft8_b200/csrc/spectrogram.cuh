@@ -35,8 +35,11 @@ __device__ __forceinline__ float2 load_sample_pair(const int16_t* a, int i) {
 }
 __device__ __forceinline__ float2 load_sample_pair(const float* a, int i) { return __ldg(reinterpret_cast<const float2*>(a + i)); }
 
+#ifndef SP_MIN_BLOCKS
+#define SP_MIN_BLOCKS 8   // 64 registers -> 8 CTAs (32 warps) per SM; measured best on B200
+#endif
 template <typename T>
-__global__ void __launch_bounds__(SP_ROWS* SP_NT)
+__global__ void __launch_bounds__(SP_ROWS* SP_NT, SP_MIN_BLOCKS)
 k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float* __restrict__ hann,
               const float2* __restrict__ W1920, const float2* __restrict__ W3840, int row_lo, int row_hi, int out_rows,
               int out_row0, int fill_row0) {
