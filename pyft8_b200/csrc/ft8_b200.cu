@@ -472,8 +472,9 @@ extern "C" int ft8_sync(ft8_handle* h, const float* grid_db, int grid_rows, int 
         }
         CK(cudaMemsetAsync(d_pay, 0, N * 58 * 8 * sizeof(float), h->stream));
         CK(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), h->stream));
+        CK(cudaMemsetAsync(h->d_counts, 0, 8 * sizeof(int32_t), h->stream));
         k_pass0<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
-            cand_state(h), (int)N, dg, grid_rows, odd_even ? 375 : 0, h->cfg.llr_sd_min, d_pay, 1, h->d_list_fine, h->d_counts, h->d_stats);
+            cand_state(h), (int)N, dg, grid_rows, odd_even ? 375 : 0, h->cfg.llr_sd_min, d_pay, 1, h->d_list_fine, h->d_counts, h->d_counts + 6, h->d_stats);
         CK(cudaGetLastError());
     }
     TRY(from_device(h, cand_f0, h->d_f0, N * 2, mem));
@@ -825,7 +826,7 @@ extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dty
     CandState cs = cand_state(h);
     // ipass 0
     k_pass0<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
-        cs, N, h->d_grid, GRID_ROWS, cycle_h0, h->cfg.llr_sd_min, nullptr, 0, h->d_list_fine, h->d_counts + 0, h->d_stats);
+        cs, N, h->d_grid, GRID_ROWS, cycle_h0, h->cfg.llr_sd_min, nullptr, 0, h->d_list_fine, h->d_counts + 0, h->d_counts + 6, h->d_stats);
     CK(cudaGetLastError()); ++launches;
     CK(cudaEventRecord(h->ev[4], h->stream));
     // ipass 1

@@ -88,7 +88,7 @@ __device__ __forceinline__ void set_result(const CandState& cs, int slot, const 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows, int cycle_h0, float sd_min,
         float* __restrict__ payload_db, int llr_only, int32_t* __restrict__ list_fine, int32_t* __restrict__ count_fine,
-        DevStats* __restrict__ stats) {
+        int32_t* __restrict__ next_slot, DevStats* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char pass_smem_raw[];
     PassSmem& sm = *reinterpret_cast<PassSmem*>(pass_smem_raw);
     load_ldpc_tables(sm.tab);
@@ -99,7 +99,17 @@ k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows
     float* llr0 = sm.llr0[wi];
     const int warps_total = gridDim.x * WARPS_PER_CTA;
     unsigned long long n_ldpc = 0, n_iter = 0, n_cand = 0, n_stop = 0, n_dec = 0;
-    for (int slot = blockIdx.x * WARPS_PER_CTA + wi; slot < n_slots; slot += warps_total) {
+    (void)warps_total;
+    // candidates cost between ~0 (sd gate, iteration-0 rejects) and 25 LDPC iterations: warps pull batches of 4 slots
+    for (int base = 0, sub = 4;; ++sub) {
+        if (sub == 4) {
+            if (lane == 0) base = atomicAdd(next_slot, 4);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            sub = 0;
+            if (base >= n_slots) break;
+        }
+        const int slot = base + sub;
+        if (slot >= n_slots) continue;
         const int cyc = slot / cs.K, rank = slot - cyc * cs.K;
         if (rank >= cs.n_cand[cyc]) continue;
         ++n_cand;
