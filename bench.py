@@ -35,6 +35,11 @@ ALG_BYTES = {
     "pass234_ldpc": 696 + 696 + 24,                 # per LDPC call
     "osd": 696 + 64,                                # per OSD call
 }
+# measured DRAM traffic per cycle (bytes) of each stage's kernels: dram__bytes_read.sum + dram__bytes_write.sum of one
+# `ncu --set full` capture at 4096 cycles/launch, divided by 4096 (profiles/r01_final_summary.md)
+NCU_DRAM_BYTES_PER_CYCLE = {"spectrogram": (1480e6 + 5960e6) / 4096, "sync": (2330e6 + 27e6) / 4096, "fine": (2730e6 + 493e6) / 4096,
+                            "pass0_ldpc5": (3540e6 + 592e6) / 4096, "osd": (541e6 + 25e6) / 4096,
+                            "cycle_spectrum": (787e6 + 369e6 + 369e6 + 731e6) / 1024}
 STAGES = ["all", "spectrogram", "sync", "cycle_spectrum", "pass0_ldpc5", "fine", "pass234_ldpc", "osd", "collect"]
 
 
@@ -263,11 +268,13 @@ def run_gpu(args, dist, rank, local, world):
     for i, name in enumerate(STAGES):
         if name in ALG_BYTES:
             ach = ALG_BYTES[name] * units[name] / (stage_ms[i] / 1e3) / 1e9 if stage_ms[i] > 0 else 0.0
+            traffic = NCU_DRAM_BYTES_PER_CYCLE.get(name)
             stages.append({"kernel": name, "ms": round(float(stage_ms[i]), 4), "share": round(float(stage_ms[i] / stage_ms[0]), 4),
-                           "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5)})
+                           "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
+                           "traffic": int(traffic * B) if traffic else None})
     dom = max(stages, key=lambda s: s["ms"])
     roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
                 "note": "dominant kernel by device time; LDPC/OSD/fine-sync stages are issue/ALU-bound, see DESIGN.md; "
                         "spectrogram and sync (the HBM-roofline stages of the north star) are in roofline_stages"}
     cpu = None
