@@ -189,54 +189,53 @@ __device__ __forceinline__ void fine_ifft(float2* dst, float2* tmp, const float2
 #endif
 }
 
-// 32-sample symbol DFT by one warp (receiver.py:195): lane m holds z[i0+m] and its twiddles tw[t] = exp(-2 pi i t m/32),
-// t < 8.  The 8 partial products are summed over the 32 lanes with a halving exchange (each step keeps half of the bins),
-// 18 shuffles instead of 80.  Returns |bin| / 3200 (numpy's ifft carries the 1/N) for bin = 4*bit4 + 2*bit3 + bit2 of the lane index;
-// the four lanes that share lane>>2 hold the same value.
+// 32-sample symbol DFTs (receiver.py:195), FOUR windows per warp: lane = 8*g + m serves window g (0..3) and holds its
+// samples m, m+8, m+16, m+24.  Since w32^(8t) = (-i)^t, summing those four samples with the bin-t kernel is a 4-point DFT
+// (bin t mod 4) times this lane's twiddle tw[t] = exp(-2 pi i t m/32); the 8 partial bins are then summed over the 8 lanes
+// of the window with a halving exchange (offsets 4, 2, 1: 14 shuffles), after which lane m holds bin m.
+// Returns |bin (lane & 7)| / 3200 of window (lane >> 3)  (numpy's ifft carries the 1/N).
 __device__ __forceinline__ float2 shfl_xor2(float2 v, int o) {
     return make_float2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
 }
 
-__device__ __forceinline__ float dft32_mag(const float2* z, int i0, int lane, const float2 (&tw)[8]) {
-    const float2 v = z[i0 + lane];
+__device__ __forceinline__ float dft32x4_mag(const float2* z, int i0, int lane, const float2 (&tw)[8]) {
+    const int m = lane & 7;
+    float2 v[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) v[a] = z[i0 + m + 8 * a];
+    Dft<4, false>::run(v);
     float2 c[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) c[t] = cmul(v, tw[t]);
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    for (int t = 0; t < 8; ++t) c[t] = cmul(v[t & 3], tw[t]);
+    const bool h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
     float2 d4[4], d2[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {                       // lanes with bit 4 clear keep bins 0..3, the others 4..7
-        const float2 send = h16 ? c[j] : c[j + 4], keep = h16 ? c[j + 4] : c[j];
-        d4[j] = cadd(keep, shfl_xor2(send, 16));
+    for (int j = 0; j < 4; ++j) {                       // lanes with bit 2 clear keep bins 0..3, the others 4..7
+        const float2 send = h4 ? c[j] : c[j + 4], keep = h4 ? c[j + 4] : c[j];
+        d4[j] = cadd(keep, shfl_xor2(send, 4));
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-        const float2 send = h8 ? d4[j] : d4[j + 2], keep = h8 ? d4[j + 2] : d4[j];
-        d2[j] = cadd(keep, shfl_xor2(send, 8));
+        const float2 send = h2 ? d4[j] : d4[j + 2], keep = h2 ? d4[j + 2] : d4[j];
+        d2[j] = cadd(keep, shfl_xor2(send, 2));
     }
-    float2 s;
-    {
-        const float2 send = h4 ? d2[0] : d2[1], keep = h4 ? d2[1] : d2[0];
-        s = cadd(keep, shfl_xor2(send, 4));
-    }
-    s = cadd(s, shfl_xor2(s, 2));
-    s = cadd(s, shfl_xor2(s, 1));
+    const float2 send = h1 ? d2[0] : d2[1], keep = h1 ? d2[1] : d2[0];
+    const float2 s = cadd(keep, shfl_xor2(send, 1));
     return sqrtf(fmaf(s.x, s.x, s.y * s.y)) * (1.0f / 3200.0f);
 }
 
 __device__ __forceinline__ int clip_start(int i) { return max(0, min(FINE_N - 32, i)); }
 
-// Weighted Costas contribution of symbol row k (middle block) for a window start tb: sum over tones 0..6 of
-// |bin| * (+1 on the Costas tone, -1/6 elsewhere), every lane gets the row total (receiver.py:198-203).
-__device__ __forceinline__ float costas_row(const float2* z, int tb, int k, int lane, const float2 (&tw)[8]) {
-    const float g = dft32_mag(z, clip_start(tb + 32 * (36 + k)), lane, tw);
-    const int bin = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+// Weighted middle-Costas sum (receiver.py:198-203) over symbol rows k0 .. k0+3 (rows >= 7 contribute nothing) for a window
+// start tb: sum over tones 0..6 of |bin| * (+1 on the Costas tone, -1/6 elsewhere).  Every lane gets the 4-row total.
+__device__ __forceinline__ float costas_rows4(const float2* z, int tb, int k0, int lane, const float2 (&tw)[8]) {
+    const int k = k0 + (lane >> 3), bin = lane & 7;
+    const float g = dft32x4_mag(z, clip_start(tb + 32 * (36 + min(k, 6))), lane, tw);
     float c = 0.0f;
-    if ((lane & 3) == 0 && bin < 7) c = (bin == c_costas[k]) ? g : g * (-1.0f / 6.0f);
-    c += __shfl_xor_sync(0xffffffffu, c, 16);
-    c += __shfl_xor_sync(0xffffffffu, c, 8);
-    c += __shfl_xor_sync(0xffffffffu, c, 4);
-    return c;                                           // lanes with (lane & 3) == 0 hold the total
+    if (k < 7 && bin < 7) c = (bin == c_costas[k]) ? g : g * (-1.0f / 6.0f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    return c;
 }
 
 constexpr int FINE_SMEM_BYTES = FINE_BUFS * FINE_N * (int)sizeof(float2) + (79 * 8 + 16 + 100) * (int)sizeof(float) + 32 * (int)sizeof(float2);
@@ -259,7 +258,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
     __syncthreads();
     float2 tw[8];                                                     // this lane's DFT32 twiddles, fixed for the kernel
 #pragma unroll
-    for (int t = 0; t < 8; ++t) tw[t] = w32[(t * lane) & 31];
+    for (int t = 0; t < 8; ++t) tw[t] = w32[(t * (lane & 7)) & 31];
     const int n_items = list ? *count : n_direct;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int slot = list ? list[item] : item;
@@ -271,9 +270,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT; warp w scores start w
         fine_ifft(fine_smem, FINE_BUFS == 3 ? fine_smem + FINE_N : fine_smem, sp, fb0, tid, W3200, taper);
         {
-            float sc = 0.0f;
-#pragma unroll 1
-            for (int k = 0; k < 7; ++k) sc += costas_row(fine_smem, tb0 - 8 + 2 * warp, k, lane, tw);
+            const float sc = costas_rows4(fine_smem, tb0 - 8 + 2 * warp, 0, lane, tw) + costas_rows4(fine_smem, tb0 - 8 + 2 * warp, 4, lane, tw);
             if (lane == 0) score[warp] = sc;
         }
         __syncthreads();
@@ -285,7 +282,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         // ---- frequency scan at the chosen time tweak (receiver.py:154-159).  The ftweak = 0 baseband is the one already
         // in buffer 0, so it is scored first and the other 8 are computed into whichever buffer does not hold the best
         // so far; "first maximum in ascending ftweak order" = larger score, or equal score and smaller index.
-        // Warp k (< 7) scores Costas symbol k; the 7 row totals are summed in order by every thread.
+        // Warps 0 and 1 score Costas symbols 0..3 and 4..6; the two partial sums are added by every thread.
         int keep = 0, best_fi = 4;
         float bestf = 0.0f;
         for (int q = -1; q < 8; ++q) {
@@ -296,23 +293,22 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
             const int cur = q < 0 ? 0 : keep ^ 1, scratch = cur;                     // best in one buffer, work in the other
 #endif
             if (q >= 0) fine_ifft(fine_smem + cur * FINE_N, fine_smem + scratch * FINE_N, sp, fb0 + (-32 + 8 * fi), tid, W3200, taper);
-            if (warp < 7) {
-                const float r = costas_row(fine_smem + cur * FINE_N, tb0 + tt, warp, lane, tw);
+            if (warp < 2) {
+                const float r = costas_rows4(fine_smem + cur * FINE_N, tb0 + tt, 4 * warp, lane, tw);
                 if (lane == 0) score[8 + warp] = r;
             }
             __syncthreads();
-            float sc = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) sc += score[8 + k];
+            const float sc = score[8] + score[9];
             if (q < 0 || sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; keep = cur; }
             __syncthreads();
         }
         const int ff = -32 + 8 * best_fi;
-        // ---- final grid from the kept baseband (receiver.py:161): one warp per symbol row
+        // ---- final grid from the kept baseband (receiver.py:161): four symbol rows per warp
         const float2* z = fine_smem + keep * FINE_N;
-        for (int j = warp; j < 79; j += FINE_NT / 32) {
-            const float g = dft32_mag(z, clip_start(tb0 + tt + 32 * j), lane, tw);
-            if ((lane & 3) == 0) G[j * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = g;
+        for (int j0 = 4 * warp; j0 < 79; j0 += 4 * (FINE_NT / 32)) {
+            const int j = j0 + (lane >> 3);
+            const float g = dft32x4_mag(z, clip_start(tb0 + tt + 32 * min(j, 78)), lane, tw);
+            if (j < 79) G[j * 8 + (lane & 7)] = g;
         }
         __syncthreads();
         if (sig_grid) for (int i = tid; i < 79 * 8; i += FINE_NT) sig_grid[(size_t)slot * 632 + i] = G[i];
