@@ -166,7 +166,8 @@ int ft8_crc14(ft8_handle* h, const uint32_t* bits91, int N, int32_t* flags, int 
 /* Whole path, Receiver.search + Candidate.decode passes 0..7 for every candidate (receiver.py:68-107, 389-398):
  * audio[B][180000] -> records.  rec has room for rec_capacity records; records of one cycle are contiguous and in
  * the reference's emission order; n_rec[B] (int32) counts per cycle; duplicates of a payload are kept with
- * emitted = 0.  The output arrays are HOST memory in every mode; `mem` describes `audio` only. */
+ * emitted = 0.  The output arrays are HOST memory in every mode; `mem` describes `audio` only.  Each cycle is decoded in
+ * isolation (no rows from a neighbouring cycle); odd_even is carried as a label only (their_tx_cycle, receiver.py:62). */
 int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even,
                       ft8_record* rec, int rec_capacity, int32_t* n_rec, int mem);
 

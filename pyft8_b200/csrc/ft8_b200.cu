@@ -774,7 +774,10 @@ extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dty
     if (!audio || !rec || !n_rec || B <= 0 || rec_capacity < 0) return fail(h, FT8_E_BADARG, "ft8_decode_cycles: bad argument");
     if ((size_t)B > h->cap_cycles) return fail(h, FT8_E_CAPACITY, "ft8_decode_cycles: B exceeds cfg.max_cycles");
     const int K = h->cfg.max_cands, N = B * K;
-    const int cycle_h0 = odd_even ? 375 : 0;
+    // every cycle of the batch is decoded in isolation on its own 376-row waterfall: the search always runs
+    // with cycle_h0 = 0; odd_even only labels the records on the host side (their_tx_cycle, receiver.py:62)
+    (void)odd_even;
+    const int cycle_h0 = 0;
     if (audio_dtype != FT8_AUDIO_I16 && audio_dtype != FT8_AUDIO_F32) return fail(h, FT8_E_BADARG, "audio_dtype must be FT8_AUDIO_I16 or FT8_AUDIO_F32");
     const size_t esz = audio_dtype == FT8_AUDIO_I16 ? 2 : 4;
     const void* da = audio;
@@ -803,7 +806,7 @@ extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dty
             const char* a = (const char*)h->d_audio + (size_t)b0 * CYCLE_SAMPLES * esz;
             CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
             TRY(launch_spectrogram(h, a, audio_dtype, nb, h->d_grid + (size_t)b0 * GRID_ROWS * GRID_COLS)); ++launches;
-            TRY(launch_sync(h, h->d_grid + (size_t)b0 * GRID_ROWS * GRID_COLS, GRID_ROWS, nb, odd_even, b0)); launches += 2;
+            TRY(launch_sync(h, h->d_grid + (size_t)b0 * GRID_ROWS * GRID_COLS, GRID_ROWS, nb, 0, b0)); launches += 2;
             TRY(launch_cycle_spectrum(h, a, audio_dtype, nb, h->d_spec + (size_t)b0 * FINE_SPEC_STRIDE, FINE_SPEC_STRIDE, FINE_SPEC_STRIDE - 1));
             launches += 2 * ((nb + (int)h->y_cycles - 1) / (int)h->y_cycles);
         }
@@ -816,7 +819,7 @@ extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dty
         TRY(launch_spectrogram(h, da, audio_dtype, B, h->d_grid)); ++launches;
         CK(cudaEventRecord(h->ev[1], h->stream));
         // S2
-        TRY(launch_sync(h, h->d_grid, GRID_ROWS, B, odd_even)); launches += 2;
+        TRY(launch_sync(h, h->d_grid, GRID_ROWS, B, 0)); launches += 2;
         CK(cudaEventRecord(h->ev[2], h->stream));
         // F1 (independent of S1/S2; same stream)
         TRY(launch_cycle_spectrum(h, da, audio_dtype, B, h->d_spec, FINE_SPEC_STRIDE, FINE_SPEC_STRIDE - 1));

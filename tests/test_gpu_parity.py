@@ -323,6 +323,13 @@ def test_decode_cycles_batch_is_per_cycle_independent(eng, golden_cycles):
     assert st["cycles"] == 4 and st["kernel_launches"] > 0 and st["decoded"] == len(rec)
 
 
+def test_decode_cycles_odd_even_is_only_a_label(eng, golden_cycles):
+    audio, g = golden_cycles["syn20"]
+    r0, _ = eng.decode_cycles(audio, odd_even=0)
+    r1, _ = eng.decode_cycles(audio, odd_even=1)
+    assert np.array_equal(r0["bits91"], r1["bits91"]) and len(r0) == len(g["dec_bits77_hex"][g["dec_bits77_hex"] != "0"])
+
+
 def test_decode_cycles_silence_and_capacity(eng):
     rec, n = eng.decode_cycles(np.zeros((2, 180000), np.int16))
     assert len(rec) == 0 and list(n) == [0, 0]
