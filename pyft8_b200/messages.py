@@ -110,3 +110,48 @@ def unpack(bits):
             ca, cb = cb, ca
         return (ca, cb, ("", "RRR", "RR73", "73")[rrr])
     return None
+
+
+# ---------------------------------------------------------------------------------------------- batch text formatting
+_TEXT_CACHE = {}
+_HASH_LO, _HASH_HI = NTOKENS, NTOKENS + MAX22 - 1      # n28 range rendered through the hash table ('<...>')
+
+
+def _history_free(bits):
+    """True when the text of this payload does not depend on the callsign-hash history (no '<...>' field)."""
+    i3, b74 = bits & 7, bits >> 3
+    if i3 not in (1, 2):
+        return False
+    a, b = (b74 >> 46) & 0xFFFFFFF, (b74 >> 17) & 0xFFFFFFF
+    return not (_HASH_LO <= a < _HASH_HI or _HASH_LO <= b < _HASH_HI)
+
+
+def unpack_many(payloads):
+    """unpack() over a sequence of 77-bit payloads, in order, with the same hash-history side effects.
+
+    Skimmer-scale output repeats payloads heavily (duplicate candidates inside a cycle, stations repeating a message in
+    consecutive cycles), so history-independent payloads are formatted once and served from a cache; payloads whose text
+    goes through the hash table are always re-evaluated."""
+    out = []
+    for b in payloads:
+        b = int(b)
+        t = _TEXT_CACHE.get(b)
+        if t is None:
+            t = unpack(b)
+            if t is not None and _history_free(b):
+                if len(_TEXT_CACHE) > 1 << 20:
+                    _TEXT_CACHE.clear()
+                _TEXT_CACHE[b] = t
+        else:
+            # keep the reference's side effect: every decoded standard call is (re-)entered in the hash table
+            for c in t[:2]:
+                if _is_plain_call(c):
+                    hs = hashes_for_calls.get(c)
+                    if hs is None or call_hashes.get(hs[2]) != c:
+                        add_call_hashes(c)
+        out.append(t)
+    return out
+
+
+def _is_plain_call(c):
+    return not (c.startswith("CQ") or c in ("DE", "QRZ") or c.startswith("<"))

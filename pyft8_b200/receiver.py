@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib as L
 from .engine import Engine, bits91_to_int
-from .messages import unpack
+from .messages import unpack, unpack_many
 from .time_utils import TimeUtils
 from . import decoders
 
@@ -242,9 +242,21 @@ class AudioIn:
         return (None, 0)
 
 
-def record_to_message(r, cyclestart_string="", band=None, odd_even=0, now=0.0):
-    """ft8_record -> the dict Candidate.check_and_package emits (receiver.py:61-64), or None if unpack rejects."""
-    msg = unpack(bits91_to_int(r["bits91"]) >> 14)
+def records_bits77(rec):
+    """77-bit payloads (python ints) of a record array, vectorised: bit j of the word is (w[j>>5] >> (j&31)) & 1, MSB first."""
+    w = np.asarray(rec["bits91"], np.uint32).reshape(-1, 3)
+    j = np.arange(77)
+    bits = (w[:, j >> 5] >> (j & 31).astype(np.uint32)) & 1                     # [n, 77], codeword order
+    hi = (bits[:, :13].astype(np.uint64) << np.arange(12, -1, -1, dtype=np.uint64)).sum(axis=1)
+    lo = (bits[:, 13:].astype(np.uint64) << np.arange(63, -1, -1, dtype=np.uint64)).sum(axis=1)
+    return [(int(h) << 64) | int(l) for h, l in zip(hi, lo)]
+
+
+def record_to_message(r, cyclestart_string="", band=None, odd_even=0, now=0.0, msg=False):
+    """ft8_record -> the dict Candidate.check_and_package emits (receiver.py:61-64), or None if unpack rejects.
+    `msg` may carry the already formatted text tuple (batch path, messages.unpack_many)."""
+    if msg is False:
+        msg = unpack(bits91_to_int(r["bits91"]) >> 14)
     if msg is None:
         return None
     src = "grid" if r["ipass"] == 0 else "fine"
@@ -362,10 +374,11 @@ class Receiver:
         rec, n = self._batch_engine.decode_cycles(a, odd_even)
         out = [[] for _ in range(B)]
         seen = [set() for _ in range(B)]
-        for r in rec:
+        texts = unpack_many(records_bits77(rec))          # in record (= emission) order: same hash history as the reference
+        for r, txt in zip(rec, texts):
             cyc = int(r["cycle"])
             cs = cyclestart_strings[cyc] if cyclestart_strings else ""
-            m = record_to_message(r, cs, self.band, odd_even, self._tu.time())
+            m = record_to_message(r, cs, self.band, odd_even, self._tu.time(), msg=txt)
             if m is None:
                 continue
             key = cs + " ".join(m["msg_tuple"])          # de-dup on text like receiver.py:53

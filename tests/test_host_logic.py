@@ -116,3 +116,33 @@ def test_gather_records_single_process():
     rec = np.zeros(3, L.RECORD_DTYPE)
     out = gather_records(rec, 7)
     assert list(out["cycle"]) == [7, 7, 7] and list(rec["cycle"]) == [0, 0, 0]
+
+
+def test_unpack_many_equals_sequential_unpack_with_hash_history():
+    rng = np.random.default_rng(21)
+    pool = [synth.pack77(*synth.random_message(rng)) for _ in range(64)]
+    messages.add_call_hashes("G1OJS")
+    h22 = messages.hashes_for_calls["G1OJS"][2][0]
+    hashed = ((2063592 + h22) << 49) | (synth.pack_call28("EA6VQ")[0] << 20) | (32403 << 3) | 1
+    g1 = synth.pack77("CQ", "G1OJS", "IO90")
+    seq = [hashed, pool[3], g1, hashed, pool[3], 0, 5, pool[7], g1, hashed] + [pool[i] for i in rng.integers(0, 64, 500)]
+    messages.call_hashes.clear()
+    messages._TEXT_CACHE.clear()
+    want = [messages.unpack(b) for b in seq]
+    assert want[0] == ("<...>", "EA6VQ", "RR73") and want[3] == ("<G1OJS>", "EA6VQ", "RR73")      # history matters
+    messages.call_hashes.clear()
+    got = messages.unpack_many(seq)
+    assert got == want
+    messages.call_hashes.clear()                      # warm cache, cold hash table: side effects are still replayed
+    assert messages.unpack_many(seq) == want
+
+
+def test_records_bits77_vectorised():
+    from pyft8_b200.receiver import records_bits77
+    rng = np.random.default_rng(4)
+    vals = [int.from_bytes(rng.bytes(12), "big") >> 5 for _ in range(100)]
+    rec = np.zeros(100, L.RECORD_DTYPE)
+    for i, v in enumerate(vals):
+        rec["bits91"][i] = int_to_bits91(v)
+    assert records_bits77(rec) == [v >> 14 for v in vals]
+    assert records_bits77(rec[:0]) == []
