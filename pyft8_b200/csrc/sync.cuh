@@ -56,25 +56,35 @@ k_sync_scores(const float* __restrict__ grid, int grid_rows, int cycle_h0, float
     const float* g = grid + (size_t)cyc * grid_rows * GRID_COLS;
     const int row0 = cycle_h0 + H0_LO + 148;    // 111 for the even cycle
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- phase A: one warp per row; lanes hold columns lane, lane+32, lane+64 (71 needed), pair sums via shuffles
-    for (int r = warp; r < SY_ROWS; r += SY_NT / 32) {
-        int row = (row0 + r) % LIVE_ROWS;
-        if (row < 0) row += LIVE_ROWS;
-        const bool stored = row < grid_rows;
-        const float* gr = g + (size_t)row * GRID_COLS + f_base;
-        float v[3];
+    // ---- phase A: one warp per row; lanes hold columns lane, lane+32, lane+64 (71 needed), pair sums via shuffles.
+    //      Rows are taken four at a time so that 12 independent global loads per lane are in flight.
+    constexpr int NW = SY_NT / 32, RB = 4;
+    for (int rb = warp * RB; rb < SY_ROWS; rb += NW * RB) {
+        float v[RB][3];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const int c = lane + 32 * q;
-            v[q] = (c < 71 && f_base + c < GRID_COLS) ? (stored ? __ldg(gr + c) : 1.0f) : 0.0f;
+        for (int u = 0; u < RB; ++u) {
+            const int r = rb + u;
+            int row = (row0 + r) % LIVE_ROWS;
+            if (row < 0) row += LIVE_ROWS;
+            const bool stored = row < grid_rows && r < SY_ROWS;
+            const float* gr = g + (size_t)row * GRID_COLS + f_base;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int c = lane + 32 * q;
+                v[u][q] = (c < 71) ? (stored ? __ldg(gr + c) : 1.0f) : 0.0f;
+            }
         }
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            float nb = __shfl_down_sync(0xffffffffu, v[q], 1);
-            const float wrap = __shfl_sync(0xffffffffu, (q < 2) ? v[q + 1] : 0.0f, 0);
-            if (lane == 31) nb = wrap;
-            const int c = lane + 32 * q;
-            if (c < 70) P2[r * SY_PW + c] = v[q] + nb;
+        for (int u = 0; u < RB; ++u) {
+            const int r = rb + u;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                float nb = __shfl_down_sync(0xffffffffu, v[u][q], 1);
+                const float wrap = __shfl_sync(0xffffffffu, (q < 2) ? v[u][q + 1] : 0.0f, 0);
+                if (lane == 31) nb = wrap;
+                const int c = lane + 32 * q;
+                if (c < 70 && r < SY_ROWS) P2[r * SY_PW + c] = v[u][q] + nb;
+            }
         }
     }
     __syncthreads();
