@@ -137,6 +137,36 @@ template <bool INV> struct Dft<16, INV> {
     }
 };
 
+// 15 = 3 x 5 in registers: j = 5*j1 + j2, k = k1 + 3*k2;  w15^(jk) = w3^(j1 k1) * w15^(j2 k1) * w5^(j2 k2)
+template <bool INV> struct Dft<15, INV> {
+    static __device__ __forceinline__ void run(float2* a) {
+        float2 c[3][5];   // c[k1][j2]
+#pragma unroll
+        for (int j2 = 0; j2 < 5; ++j2) {
+            float2 t[3] = {a[j2], a[5 + j2], a[10 + j2]};
+            Dft<3, INV>::run(t);
+#pragma unroll
+            for (int k1 = 0; k1 < 3; ++k1) c[k1][j2] = t[k1];
+        }
+#define FT8_TW15(v, wr, wi) v = INV ? cmulc(v, make_float2(wr, wi)) : cmul(v, make_float2(wr, wi))
+        FT8_TW15(c[1][1], 0.91354545764260087f, -0.40673664307580015f);
+        FT8_TW15(c[1][2], 0.66913060635885824f, -0.74314482547739413f);
+        FT8_TW15(c[1][3], 0.30901699437494745f, -0.95105651629515353f);
+        FT8_TW15(c[1][4], -0.10452846326765333f, -0.9945218953682734f);
+        FT8_TW15(c[2][1], 0.66913060635885824f, -0.74314482547739413f);
+        FT8_TW15(c[2][2], -0.10452846326765333f, -0.9945218953682734f);
+        FT8_TW15(c[2][3], -0.80901699437494734f, -0.58778525229247325f);
+        FT8_TW15(c[2][4], -0.97814760073380569f, 0.20791169081775907f);
+#undef FT8_TW15
+#pragma unroll
+        for (int k1 = 0; k1 < 3; ++k1) {
+            Dft<5, INV>::run(c[k1]);
+#pragma unroll
+            for (int k2 = 0; k2 < 5; ++k2) a[k1 + 3 * k2] = c[k1][k2];
+        }
+    }
+};
+
 // One Stockham pass for butterfly t (0 <= t < N/R).  x, y may be any addressable memory.
 // W is the length-N twiddle table (W[j] = exp(-2 pi i j / N)), read through the read-only path.
 template <int N, int R, int S> struct Pass {
@@ -190,8 +220,7 @@ struct CtaSync {
 
 // Complete in-place transforms for the sizes on the path (NT threads cooperate, CTA-wide barriers).
 template <int NT, bool INV> __device__ __forceinline__ void fft1920(float2* buf, int lt, const float2* __restrict__ W) {
-    pass_inplace<1920, 3, 1, NT, INV>(buf, lt, W, CtaSync());
-    pass_inplace<1920, 5, 3, NT, INV>(buf, lt, W, CtaSync());
+    pass_inplace<1920, 15, 1, NT, INV>(buf, lt, W, CtaSync());
     pass_inplace<1920, 8, 15, NT, INV>(buf, lt, W, CtaSync());
     pass_inplace<1920, 16, 120, NT, INV>(buf, lt, W, CtaSync());
 }

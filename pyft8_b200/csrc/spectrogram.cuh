@@ -6,7 +6,7 @@
 // with x = 0 before the cycle start and grid[0, :] = 1.0 (the reference's initial fill).
 //
 // One group of 128 threads per row, SP_ROWS rows per CTA (1 measured best on B200: 5.4 vs 6.1 ms / 2048 cycles for 4).  The 3840-point real transform is a
-// 1920-point complex Stockham FFT of z[n] = x[2n] + i*x[2n+1] in shared memory (passes 3,5,8,16);
+// 1920-point complex Stockham FFT of z[n] = x[2n] + i*x[2n+1] in shared memory (passes 15,8,16);
 // the first pass reads the windowed audio straight from global memory (int16 -> fp32 fused), the
 // epilogue untangles only the 976 bins that are kept and writes dB.  Rows of one CTA are adjacent,
 // so their 7/8-overlapping windows hit L1/L2: HBM sees the audio once and the grid once.
@@ -20,11 +20,8 @@ namespace ft8 {
 #ifndef SP_ROWS_N
 #define SP_ROWS_N 1
 #endif
-#ifndef SP_PINGPONG
-#define SP_PINGPONG 0
-#endif
 constexpr int SP_ROWS = SP_ROWS_N;  // rows per CTA
-constexpr int SP_BUFS = SP_PINGPONG ? 2 : 1;
+constexpr int SP_BUFS = 1;          // one in-place buffer per row (ping-pong buffers measured slower)
 constexpr int SP_NT = 128;          // threads per row
 constexpr int GRID_ROWS = 376, GRID_COLS = 976, CYCLE_SAMPLES = 180000, NFFT_S = 3840, HOP = 480;
 
@@ -56,37 +53,26 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
     }
     const int s0 = HOP * h - NFFT_S;      // first sample of the window (may be negative)
 
-    // pass (R=3, S=1) with operands gathered from global memory: z[n] for n = p + 640*j
+    // pass (R=15, S=1, M=128) with operands gathered from global memory: butterfly p = lt reads z[p + 128 j], j < 15 --
+    // exactly one butterfly per thread, radix 15 = 3 x 5 in registers
     {
-        constexpr int NBF = 640, PER = NBF / SP_NT;
-        float2 a[PER][3];
+        float2 a[15];
 #pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int p = lt + i * SP_NT;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int n = p + 640 * j;
-                const int si = s0 + 2 * n;
-                float2 z = make_float2(0.f, 0.f);
-                if (live && si >= 0) {                      // si is even: the pair never straddles the cycle start
-                    const float2 w = __ldg(reinterpret_cast<const float2*>(hann + 2 * n));
-                    const float2 v = load_sample_pair(x, si);
-                    z = make_float2(v.x * w.x, v.y * w.y);
-                }
-                a[i][j] = z;
+        for (int j = 0; j < 15; ++j) {
+            const int n = lt + 128 * j;
+            const int si = s0 + 2 * n;
+            float2 z = make_float2(0.f, 0.f);
+            if (live && si >= 0) {                      // si is even: the pair never straddles the cycle start
+                const float2 w = __ldg(reinterpret_cast<const float2*>(hann + 2 * n));
+                const float2 v = load_sample_pair(x, si);
+                z = make_float2(v.x * w.x, v.y * w.y);
             }
+            a[j] = z;
         }
-#pragma unroll
-        for (int i = 0; i < PER; ++i) Pass<1920, 3, 1>::template compute_store<false>(buf, lt + i * SP_NT, a[i], W1920);
+        Pass<1920, 15, 1>::template compute_store<false>(buf, lt, a, W1920);
         __syncthreads();
     }
-#if SP_PINGPONG
-    pass_oop<1920, 5, 3, SP_NT, false>(buf, buf + 1920, lt, W1920);
-    pass_oop<1920, 8, 15, SP_NT, false>(buf + 1920, buf, lt, W1920);
-#else
-    pass_inplace<1920, 5, 3, SP_NT, false>(buf, lt, W1920, CtaSync());
     pass_inplace<1920, 8, 15, SP_NT, false>(buf, lt, W1920, CtaSync());
-#endif
     pass_oop<1920, 16, 120, SP_NT, false>(buf, buf, lt, W1920);   // last pass (M = 1): each thread rewrites the 16 positions it read
 
     // untangle the real transform for bins 0..975 and write dB
