@@ -393,3 +393,55 @@ def test_parity_sweep_device_generated_batch(eng):
         want = [x["bits77"] for x in o.decode_cycle(host[b])[0]]
         assert set(got) == set(want), b
         assert len(got) == len(set(got))
+
+
+def test_engine_configuration_knobs(golden_cycles):
+    """Receiver(sync_score_min, max_cands) and osd flip counts are honoured like the reference's keyword arguments."""
+    audio, g = golden_cycles["test_09"]
+    grid = o.spectrogram(audio)
+    for score_min, max_cands in ((85, 50), (100, 200), (60, 300)):
+        e = Engine(max_cycles=1, max_cands=max_cands, sync_score_min=score_min)
+        f0, h0, sc, n, _ = e.sync(grid, want_payload=False)
+        fo, ho, so, _ = o.search(grid, score_min, max_cands)
+        assert int(n[0]) == len(fo) and np.array_equal(f0[0, :len(fo)], fo) and np.array_equal(h0[0, :len(fo)], ho)
+        rec, cnt = e.decode_cycles(audio)
+        ref = o.decode_cycle(audio, score_min, max_cands)[0]
+        got = [bits91_to_int(r["bits91"]) >> 14 for r in rec[rec["emitted"] == 1]]
+        assert got == [r["bits77"] for r in ref]
+        e.close()
+
+
+def test_float32_audio_and_two_engines_concurrently(golden_cycles):
+    import threading
+    a8, g8 = golden_cycles["test_08"]
+    a9, g9 = golden_cycles["test_09"]
+    engs = [Engine(max_cycles=2), Engine(max_cycles=2)]
+    out = [None, None]
+
+    def run(i, a):
+        out[i] = engs[i].decode_cycles(np.stack([a, a]).astype(np.float32))
+    th = [threading.Thread(target=run, args=(0, a8)), threading.Thread(target=run, args=(1, a9))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for (rec, cnt), g in zip(out, (g8, g9)):
+        for b in range(2):
+            em = rec[(rec["cycle"] == b) & (rec["emitted"] == 1)]
+            assert ["%x" % (bits91_to_int(r["bits91"]) >> 14) for r in em] == list(g["msg_bits77_hex"])
+    [e.close() for e in engs]
+
+
+def test_error_paths_raise_with_message(eng):
+    with pytest.raises(RuntimeError, match="singleflips"):
+        eng.osd(np.zeros((1, 174), np.float32), singleflips=92)
+    import ctypes as C
+    z = np.zeros(8, np.float32)
+    p = z.ctypes.data_as(C.c_void_p)
+    rc = eng._lib.ft8_sync(eng._h, p, 100, 1, 0, p, p, p, p, None, 0)          # grid_rows must be 376 or 750
+    assert rc == L.E_BADARG and b"grid_rows" in eng._lib.ft8_last_error(eng._h)
+    assert eng._lib.ft8_spectrogram(eng._h, None, 0, 1, p, 0) == L.E_BADARG     # NULL pointer
+    with pytest.raises(ValueError):
+        eng.spectrogram(np.zeros((1, 180000), np.float64))
+    with pytest.raises(RuntimeError, match="n must be"):
+        eng.debug_fft(np.zeros((1, 100), np.complex64))
+    with pytest.raises(RuntimeError, match="max_cycles"):
+        eng.spectrogram(np.zeros((9, 180000), np.int16))
