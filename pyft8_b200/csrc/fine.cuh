@@ -27,9 +27,7 @@ namespace ft8 {
 constexpr int CS_N = 96000, CS_N1 = 375, CS_N2 = 256, CS_COLS = 16, CS_NT = 256;
 constexpr int FINE_SPEC_STRIDE = 49152;
 constexpr int FINE_N = 3200, FINE_NT = 256;
-#ifndef FINE_BUFS
-#define FINE_BUFS 3        // 3: ping-pong passes, 2 CTAs/SM; 2: in-place middle passes, 3 CTAs/SM
-#endif
+#define FINE_BUFS 3        // best-so-far + baseband being built + FFT scratch (2-buffer variants measured 11 % slower)
 
 template <typename T> __device__ __forceinline__ float2 load_pair(const T* x, int n);
 template <> __device__ __forceinline__ float2 load_pair<int16_t>(const int16_t* x, int n) {
@@ -140,8 +138,8 @@ struct FineOut {               // per candidate
 // spec[fb + i - 3200] for i >= 3050 (taper on [3050,3150)), zero elsewhere.  First pass (R=5, S=1, M=640) reads the
 // operands a[p + 640 j] straight from the spectrum: j = 2, 3 are always zero, j = 1 is non-zero only for p < 210 and
 // j = 4 only for p >= 490, so the radix-5 butterfly degenerates to b_k = a0 + a1 w^k + a4 conj(w^k), w = e^{+2 pi i/5}.
-__device__ __forceinline__ void fine_ifft(float2* dst, float2* tmp, const float2* __restrict__ spec, int fb, int tid,
-                                          const float2* __restrict__ W3200, const float* taper) {
+__device__ __forceinline__ void fine_pass1(float2* tmp, const float2* __restrict__ spec, int fb, int tid,
+                                           const float2* __restrict__ W3200, const float* taper) {
     constexpr int NBF = 640;
 #pragma unroll
     for (int p0 = 0; p0 < NBF; p0 += FINE_NT) {
@@ -175,18 +173,13 @@ __device__ __forceinline__ void fine_ifft(float2* dst, float2* tmp, const float2
             for (int k = 1; k < 5; ++k) tmp[5 * p + k] = cmulc(b[k], __ldg(&W3200[p * k]));
         }
     }
-    __syncthreads();
-#if FINE_BUFS == 3
+}
+
+// passes (5,5) (8,25) (16,200): tmp -> dst -> tmp -> dst, one barrier after each
+__device__ __forceinline__ void fine_pass234(float2* tmp, float2* dst, int tid, const float2* __restrict__ W3200) {
     pass_oop<3200, 5, 5, FINE_NT, true>(tmp, dst, tid, W3200);
     pass_oop<3200, 8, 25, FINE_NT, true>(dst, tmp, tid, W3200);
     pass_oop<3200, 16, 200, FINE_NT, true>(tmp, dst, tid, W3200);
-#else
-    // two-buffer variant: tmp == dst; middle passes are staged through registers (read all, barrier, write, barrier),
-    // the last pass (M = 1) is naturally in place: every thread reads and writes the same 16 positions
-    pass_inplace<3200, 5, 5, FINE_NT, true>(dst, tid, W3200, CtaSync());
-    pass_inplace<3200, 8, 25, FINE_NT, true>(dst, tid, W3200, CtaSync());
-    pass_oop<3200, 16, 200, FINE_NT, true>(dst, dst, tid, W3200);
-#endif
 }
 
 // 32-sample symbol DFTs (receiver.py:195), FOUR windows per warp: lane = 8*g + m serves window g (0..3) and holds its
@@ -242,7 +235,7 @@ constexpr int FINE_SMEM_BYTES = FINE_BUFS * FINE_N * (int)sizeof(float2) + (79 *
 
 // One CTA per work item (grid-stride over list[0..*count)).  cand arrays are indexed by the global slot id.
 // spec: [B][spec_stride] float2.  Outputs per slot: fo[slot], llr_fine[slot][174], optional sig_grid[slot][79][8].
-__global__ void __launch_bounds__(FINE_NT, FINE_BUFS == 3 ? 2 : 3)
+__global__ void __launch_bounds__(FINE_NT, 2)
 k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restrict__ list, const int32_t* __restrict__ count,
        int n_direct, const int32_t* __restrict__ cycle_of, const int16_t* __restrict__ cand_f0,
        const int16_t* __restrict__ cand_h0, const float2* __restrict__ W3200, FineOut* __restrict__ fo,
@@ -267,40 +260,40 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         const float2* sp = spec + (size_t)cyc * spec_stride;
         const int fb0 = 50 * f0;                                   // int(0.5 + 16*fHz), fHz = 3.125*f0
         const int tb0 = (h0 >= 0) ? 8 * h0 : 8 * h0 + 1;           // int(0.5 + 200*tsec) truncates toward zero
+        // Buffers: B0/B1 hold a finished baseband (the best so far and the one being built), T is FFT scratch.
+        // The cheap first pass of the NEXT transform (global -> T) is issued in the same barrier phase as the scoring of
+        // the current one (2 of 8 warps), so scoring adds no phase of its own.
+        float2* const T = fine_smem + 2 * FINE_N;
         // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT; warp w scores start w
-        fine_ifft(fine_smem, FINE_BUFS == 3 ? fine_smem + FINE_N : fine_smem, sp, fb0, tid, W3200, taper);
+        fine_pass1(T, sp, fb0, tid, W3200, taper);
+        __syncthreads();
+        fine_pass234(T, fine_smem, tid, W3200);
         {
             const float sc = costas_rows4(fine_smem, tb0 - 8 + 2 * warp, 0, lane, tw) + costas_rows4(fine_smem, tb0 - 8 + 2 * warp, 4, lane, tw);
             if (lane == 0) score[warp] = sc;
         }
+        fine_pass1(T, sp, fb0 - 32, tid, W3200, taper);              // first frequency tweak, overlapped with the time scan
         __syncthreads();
         int tt = -8;
-        {
-            float best = score[0];
-            for (int ti = 1; ti < 8; ++ti) if (score[ti] > best) { best = score[ti]; tt = -8 + 2 * ti; }   // first maximum
-        }
-        // ---- frequency scan at the chosen time tweak (receiver.py:154-159).  The ftweak = 0 baseband is the one already
-        // in buffer 0, so it is scored first and the other 8 are computed into whichever buffer does not hold the best
-        // so far; "first maximum in ascending ftweak order" = larger score, or equal score and smaller index.
-        // Warps 0 and 1 score Costas symbols 0..3 and 4..6; the two partial sums are added by every thread.
+        float bestf = score[0];
+        for (int ti = 1; ti < 8; ++ti) if (score[ti] > bestf) { bestf = score[ti]; tt = -8 + 2 * ti; }   // first maximum
+        // ---- frequency scan at the chosen time tweak (receiver.py:154-159).  The ftweak = 0 evaluation is the time-scan
+        // score at tt (same baseband, same window starts), already in B0; the other 8 are built into the buffer that
+        // does not hold the best so far.  "First maximum in ascending ftweak order" = larger score, or equal score and
+        // smaller index.  Warps 0 and 1 score Costas symbols 0..3 and 4..6.
         int keep = 0, best_fi = 4;
-        float bestf = 0.0f;
-        for (int q = -1; q < 8; ++q) {
-            const int fi = q < 0 ? 4 : (q < 4 ? q : q + 1);
-#if FINE_BUFS == 3
-            const int cur = q < 0 ? 0 : (keep + 1) % 3, scratch = (keep + 2) % 3;   // the three buffers rotate around the best
-#else
-            const int cur = q < 0 ? 0 : keep ^ 1, scratch = cur;                     // best in one buffer, work in the other
-#endif
-            if (q >= 0) fine_ifft(fine_smem + cur * FINE_N, fine_smem + scratch * FINE_N, sp, fb0 + (-32 + 8 * fi), tid, W3200, taper);
+        for (int e = 0; e < 8; ++e) {
+            const int fi = e < 4 ? e : e + 1;
+            float2* const cur = fine_smem + (keep ^ 1) * FINE_N;
+            fine_pass234(T, cur, tid, W3200);
             if (warp < 2) {
-                const float r = costas_rows4(fine_smem + cur * FINE_N, tb0 + tt, 4 * warp, lane, tw);
+                const float r = costas_rows4(cur, tb0 + tt, 4 * warp, lane, tw);
                 if (lane == 0) score[8 + warp] = r;
             }
+            if (e < 7) fine_pass1(T, sp, fb0 + (-32 + 8 * (e + 1 < 4 ? e + 1 : e + 2)), tid, W3200, taper);
             __syncthreads();
             const float sc = score[8] + score[9];
-            if (q < 0 || sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; keep = cur; }
-            __syncthreads();
+            if (sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; keep ^= 1; }
         }
         const int ff = -32 + 8 * best_fi;
         // ---- final grid from the kept baseband (receiver.py:161): four symbol rows per warp
