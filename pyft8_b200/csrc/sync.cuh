@@ -156,27 +156,31 @@ k_sync_scores(const float* __restrict__ grid, int grid_rows, int cycle_h0, float
 }
 
 // One CTA per cycle: stable descending rank of the f0 bins whose best score > score_min; first max_cands kept.
+// The bins above threshold are first compacted in f0 order (ballot scan), so the rank-counting loop runs over them only
+// and "ties keep ascending f0" (Python's stable sort, receiver.py:366) becomes "ties keep compacted position".
 __global__ void __launch_bounds__(960)
 k_topk(const float* __restrict__ best_score, const int16_t* __restrict__ best_h0, float score_min, int max_cands,
        int16_t* __restrict__ cand_f0, int16_t* __restrict__ cand_h0, float* __restrict__ cand_score,
        int32_t* __restrict__ n_cand) {
     __shared__ float sc[N_F0];
-    __shared__ int n_valid;
-    const int cyc = blockIdx.x, i = threadIdx.x;
-    if (i == 0) n_valid = 0;
-    float mine = 0.f;
-    if (i < N_F0) {
-        mine = best_score[(size_t)cyc * N_F0 + i];
-        sc[i] = (mine > score_min) ? mine : -1.0f;     // scores are > 0 when valid
-    }
+    __shared__ int wcount[32];
+    const int cyc = blockIdx.x, i = threadIdx.x, lane = i & 31, w = i >> 5;
+    const float mine = (i < N_F0) ? best_score[(size_t)cyc * N_F0 + i] : 0.0f;
+    const bool valid = (i < N_F0) && (mine > score_min);
+    const uint32_t m = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) wcount[w] = __popc(m);
     __syncthreads();
-    if (i < N_F0 && mine > score_min) {
+    int base = 0, total = 0;
+    for (int k = 0; k < 30; ++k) { const int c = wcount[k]; if (k < w) base += c; total += c; }
+    const int pos = base + __popc(m & ((1u << lane) - 1u));
+    if (valid) sc[pos] = mine;
+    __syncthreads();
+    if (valid) {
         int rank = 0;
-        for (int j = 0; j < N_F0; ++j) {
+        for (int j = 0; j < total; ++j) {
             const float s = sc[j];
-            rank += (s > mine || (s == mine && j < i)) ? 1 : 0;
+            rank += (s > mine || (s == mine && j < pos)) ? 1 : 0;
         }
-        atomicAdd(&n_valid, 1);
         if (rank < max_cands) {
             const size_t o = (size_t)cyc * max_cands + rank;
             cand_f0[o] = (int16_t)(F0_LO + i);
@@ -184,8 +188,7 @@ k_topk(const float* __restrict__ best_score, const int16_t* __restrict__ best_h0
             cand_score[o] = mine;
         }
     }
-    __syncthreads();
-    if (i == 0) n_cand[cyc] = min(n_valid, max_cands);
+    if (i == 0) n_cand[cyc] = min(total, max_cands);
 }
 
 // Max-log LLRs of one 58x8 payload held by a warp: lanes 0..28 own symbols lane and lane+29.
