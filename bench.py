@@ -128,6 +128,14 @@ def cpu_pool(cores):
     return _POOL
 
 
+def _host_cycle0(p):
+    sys.path.insert(0, ROOT)
+    from pyft8_b200 import workload
+    p = dict(p)
+    p["seed"] = (p["seed"] << 8) ^ int(p["pick"][0, 0]) ^ (int(p["pick"][0, 1]) << 10)     # distinct noise per cycle
+    return workload.host_cycle(p, 0)
+
+
 def cpu_rate(cycles, cores):
     """The oracle port on `cores` worker processes, one cycle at a time each: (cycles/s, ldpc calls/s, detail)."""
     pool = cpu_pool(cores)
@@ -146,8 +154,11 @@ def run_reference(args, dist, rank, world):
     from pyft8_b200 import workload
     cores = os.cpu_count() or 1
     per_step = cores * args.ref_cycles_per_core
-    params = workload.make_params(WORKLOAD, per_step * (args.steps + args.warmup), seed=args.seed)
-    cyc = [workload.host_cycle(params, b) for b in range(per_step * (args.steps + args.warmup))]
+    n_cyc = per_step * (args.steps + args.warmup)
+    params = workload.make_params(WORKLOAD, n_cyc, seed=args.seed)
+    # the numpy modulator needs ~0.8 s per 50-signal cycle: build the inputs on the worker pool too (outside the timed region)
+    small = [{k: (v[b:b + 1] if isinstance(v, np.ndarray) else v) for k, v in params.items() if k != "pool_bits77"} for b in range(n_cyc)]
+    cyc = cpu_pool(cores).map(_host_cycle0, small, chunksize=1)
     for w in range(args.warmup):
         cpu_rate(cyc[w * per_step:(w + 1) * per_step], cores)
     t0 = time.time()
