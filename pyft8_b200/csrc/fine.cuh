@@ -175,11 +175,30 @@ __device__ __forceinline__ void fine_pass1(float2* tmp, const float2* __restrict
     }
 }
 
-// passes (5,5) (8,25) (16,200): tmp -> dst -> tmp -> dst, one barrier after each
-__device__ __forceinline__ void fine_pass234(float2* tmp, float2* dst, int tid, const float2* __restrict__ W3200) {
-    pass_oop<3200, 5, 5, FINE_NT, true>(tmp, dst, tid, W3200);
-    pass_oop<3200, 8, 25, FINE_NT, true>(dst, tmp, tid, W3200);
-    pass_oop<3200, 16, 200, FINE_NT, true>(tmp, dst, tid, W3200);
+// passes (5,5) (8,25): a -> b -> a, one barrier after each; `a` then holds the operands of the last pass (16,200)
+__device__ __forceinline__ void fine_pass23(float2* a, float2* b, int tid, const float2* __restrict__ W3200) {
+    pass_oop<3200, 5, 5, FINE_NT, true>(a, b, tid, W3200);
+    pass_oop<3200, 8, 25, FINE_NT, true>(b, a, tid, W3200);
+}
+
+// Last pass (16,200) restricted to the `len` <= 256 consecutive output samples n0 .. n0+len-1 that the Costas scoring
+// reads (7 symbols x 32 samples, + 14 for the time scan): z[n] = sum_j x[n%200 + 200 j] * e^{+2 pi i j (n/200)/16}.
+// A full pass would produce 3200 samples of which the score uses 7 %; only the winning transform gets the full pass.
+__device__ __forceinline__ void fine_pass4_window(const float2* x, float2* zwin, int n0, int len, int tid, const float2* w16) {
+    if (tid < len) {
+        const int n = n0 + tid;
+        const int kk = n / 200, q = n - 200 * kk;
+        float2 acc = x[q];
+#pragma unroll
+        for (int j = 1; j < 16; ++j) {
+            const float2 w = w16[(j * kk) & 15];
+            const float2 v = x[q + 200 * j];
+            acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
+            acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
+        }
+        zwin[tid] = acc;
+    }
+    __syncthreads();
 }
 
 // 32-sample symbol DFTs (receiver.py:195), FOUR windows per warp: lane = 8*g + m serves window g (0..3) and holds its
@@ -221,9 +240,10 @@ __device__ __forceinline__ int clip_start(int i) { return max(0, min(FINE_N - 32
 
 // Weighted middle-Costas sum (receiver.py:198-203) over symbol rows k0 .. k0+3 (rows >= 7 contribute nothing) for a window
 // start tb: sum over tones 0..6 of |bin| * (+1 on the Costas tone, -1/6 elsewhere).  Every lane gets the 4-row total.
-__device__ __forceinline__ float costas_rows4(const float2* z, int tb, int k0, int lane, const float2 (&tw)[8]) {
+// `z0` = index in z of the first sample of Costas symbol 0 of the block.
+__device__ __forceinline__ float costas_rows4(const float2* z, int z0, int k0, int lane, const float2 (&tw)[8]) {
     const int k = k0 + (lane >> 3), bin = lane & 7;
-    const float g = dft32x4_mag(z, clip_start(tb + 32 * (36 + min(k, 6))), lane, tw);
+    const float g = dft32x4_mag(z, z0 + 32 * min(k, 6), lane, tw);
     float c = 0.0f;
     if (k < 7 && bin < 7) c = (bin == c_costas[k]) ? g : g * (-1.0f / 6.0f);
 #pragma unroll
@@ -231,7 +251,7 @@ __device__ __forceinline__ float costas_rows4(const float2* z, int tb, int k0, i
     return c;
 }
 
-constexpr int FINE_SMEM_BYTES = FINE_BUFS * FINE_N * (int)sizeof(float2) + (79 * 8 + 16 + 100) * (int)sizeof(float) + 32 * (int)sizeof(float2);
+constexpr int FINE_SMEM_BYTES = FINE_BUFS * FINE_N * (int)sizeof(float2) + (79 * 8 + 16 + 100) * (int)sizeof(float) + (32 + 16 + 256) * (int)sizeof(float2);
 
 // One CTA per work item (grid-stride over list[0..*count)).  cand arrays are indexed by the global slot id.
 // spec: [B][spec_stride] float2.  Outputs per slot: fo[slot], llr_fine[slot][174], optional sig_grid[slot][79][8].
@@ -244,9 +264,12 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
     float* G = reinterpret_cast<float*>(fine_smem + FINE_BUFS * FINE_N);      // [79][8]
     float* score = G + 79 * 8;                                        // [16]
     float* taper = score + 16;                                        // [100]
-    float2* w32 = reinterpret_cast<float2*>(taper + 100);             // [32]
+    float2* w32 = reinterpret_cast<float2*>(taper + 100);             // [32]  exp(-2 pi i m/32)
+    float2* w16 = w32 + 32;                                           // [16]  exp(+2 pi i m/16)
+    float2* zwin = w16 + 16;                                          // [256] scoring window of the current transform
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 32) w32[tid] = c_fine.w32[tid];
+    if (tid < 16) { const float2 w = c_fine.w32[2 * tid]; w16[tid] = make_float2(w.x, -w.y); }
     if (tid < 100) taper[tid] = c_fine.taper[tid];
     __syncthreads();
     float2 tw[8];                                                     // this lane's DFT32 twiddles, fixed for the kernel
@@ -260,44 +283,50 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         const float2* sp = spec + (size_t)cyc * spec_stride;
         const int fb0 = 50 * f0;                                   // int(0.5 + 16*fHz), fHz = 3.125*f0
         const int tb0 = (h0 >= 0) ? 8 * h0 : 8 * h0 + 1;           // int(0.5 + 200*tsec) truncates toward zero
-        // Buffers: B0/B1 hold a finished baseband (the best so far and the one being built), T is FFT scratch.
-        // The cheap first pass of the NEXT transform (global -> T) is issued in the same barrier phase as the scoring of
-        // the current one (2 of 8 warps), so scoring adds no phase of its own.
-        float2* const T = fine_smem + 2 * FINE_N;
-        // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT; warp w scores start w
-        fine_pass1(T, sp, fb0, tid, W3200, taper);
+        // Three 3200-sample buffers rotate: pb = last-pass operands of the best transform so far, pc/pf = work.
+        // Per transform: first pass (global -> pc), passes (5,5),(8,25) (pc -> pf -> pc), then only the samples the
+        // Costas score reads are produced by the windowed last pass.  The cheap first pass of the NEXT transform shares
+        // a barrier phase with the scoring of the current one (2 of 8 warps).
+        float2 *pb = fine_smem, *pc = fine_smem + FINE_N, *pf = fine_smem + 2 * FINE_N;
+        // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT; warp w scores start w.
+        //      Middle-Costas windows start at tb0 + tt + 32*(36+k) in [849, 2082] for every reachable h0: never clipped.
+        fine_pass1(pc, sp, fb0, tid, W3200, taper);
         __syncthreads();
-        fine_pass234(T, fine_smem, tid, W3200);
+        fine_pass23(pc, pf, tid, W3200);
+        fine_pass4_window(pc, zwin, tb0 - 8 + 1152, 238, tid, w16);
         {
-            const float sc = costas_rows4(fine_smem, tb0 - 8 + 2 * warp, 0, lane, tw) + costas_rows4(fine_smem, tb0 - 8 + 2 * warp, 4, lane, tw);
+            const float sc = costas_rows4(zwin, 2 * warp, 0, lane, tw) + costas_rows4(zwin, 2 * warp, 4, lane, tw);
             if (lane == 0) score[warp] = sc;
         }
-        fine_pass1(T, sp, fb0 - 32, tid, W3200, taper);              // first frequency tweak, overlapped with the time scan
+        fine_pass1(pf, sp, fb0 - 32, tid, W3200, taper);             // first frequency tweak, overlapped with the time scan
         __syncthreads();
         int tt = -8;
         float bestf = score[0];
         for (int ti = 1; ti < 8; ++ti) if (score[ti] > bestf) { bestf = score[ti]; tt = -8 + 2 * ti; }   // first maximum
         // ---- frequency scan at the chosen time tweak (receiver.py:154-159).  The ftweak = 0 evaluation is the time-scan
-        // score at tt (same baseband, same window starts), already in B0; the other 8 are built into the buffer that
-        // does not hold the best so far.  "First maximum in ascending ftweak order" = larger score, or equal score and
-        // smaller index.  Warps 0 and 1 score Costas symbols 0..3 and 4..6.
-        int keep = 0, best_fi = 4;
+        // score at tt (same baseband, same window starts); the other 8 are built in the two buffers that do not hold the
+        // best so far.  "First maximum in ascending ftweak order" = larger score, or equal score and smaller index.
+        // Warps 0 and 1 score Costas symbols 0..3 and 4..6.
+        { float2* t = pb; pb = pc; pc = pf; pf = t; }                 // best = ftweak 0; pc = first-pass output; pf = free
+        int best_fi = 4;
         for (int e = 0; e < 8; ++e) {
             const int fi = e < 4 ? e : e + 1;
-            float2* const cur = fine_smem + (keep ^ 1) * FINE_N;
-            fine_pass234(T, cur, tid, W3200);
+            fine_pass23(pc, pf, tid, W3200);                           // pc: last-pass operands of this transform
+            fine_pass4_window(pc, zwin, tb0 + tt + 1152, 224, tid, w16);
             if (warp < 2) {
-                const float r = costas_rows4(cur, tb0 + tt, 4 * warp, lane, tw);
+                const float r = costas_rows4(zwin, 0, 4 * warp, lane, tw);
                 if (lane == 0) score[8 + warp] = r;
             }
-            if (e < 7) fine_pass1(T, sp, fb0 + (-32 + 8 * (e + 1 < 4 ? e + 1 : e + 2)), tid, W3200, taper);
+            if (e < 7) fine_pass1(pf, sp, fb0 + (-32 + 8 * (e + 1 < 4 ? e + 1 : e + 2)), tid, W3200, taper);
             __syncthreads();
             const float sc = score[8] + score[9];
-            if (sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; keep ^= 1; }
+            if (sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; float2* t = pb; pb = pc; pc = t; }
+            { float2* t = pc; pc = pf; pf = t; }                       // pc = next first-pass output, pf = free
         }
         const int ff = -32 + 8 * best_fi;
-        // ---- final grid from the kept baseband (receiver.py:161): four symbol rows per warp
-        const float2* z = fine_smem + keep * FINE_N;
+        // ---- full last pass of the winner, then the final grid (receiver.py:161): four symbol rows per warp
+        pass_oop<3200, 16, 200, FINE_NT, true>(pb, pf, tid, W3200);
+        const float2* z = pf;
         for (int j0 = 4 * warp; j0 < 79; j0 += 4 * (FINE_NT / 32)) {
             const int j = j0 + (lane >> 3);
             const float g = dft32x4_mag(z, clip_start(tb0 + tt + 32 * min(j, 78)), lane, tw);

@@ -535,6 +535,10 @@ extern "C" int ft8_fine(ft8_handle* h, const float* spec, int B, const int32_t* 
     ENTER(h);
     if (!spec || !cycle_of || !f0_idx || !h0_idx || !ttweak || !ftweak || !nsync || !llr || !sd || !snr || N <= 0 || B <= 0)
         return fail(h, FT8_E_BADARG, "ft8_fine: bad argument");
+    if (mem == FT8_MEM_HOST)
+        for (int i = 0; i < N; ++i)
+            if (h0_idx[i] < -100 || h0_idx[i] > 200 || f0_idx[i] < 4 || f0_idx[i] > 1880 || cycle_of[i] < 0 || cycle_of[i] >= B)
+                return fail(h, FT8_E_BADARG, "ft8_fine: candidate outside the supported range (-100 <= h0 <= 200, 4 <= f0 <= 1880)");
     const size_t specn = (size_t)B * FT8_SPEC_BINS;
     size_t need = specn * 8 + (size_t)N * (4 + 2 + 2 + sizeof(FineOut) + 174 * 4 + 632 * 4) + 8 * 256;
     TRY(ensure_arena(h, need));
