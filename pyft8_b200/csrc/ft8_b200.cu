@@ -261,8 +261,8 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
     h->y_cycles = std::min<size_t>(B, 1024);   // four-step scratch: 768 KB per cycle
     CKC(dmalloc(&h->d_Y, h->y_cycles * CS_N));
     CKC(dmalloc(&h->d_spec, B * FINE_SPEC_STRIDE));
-    CKC(dmalloc(&h->d_best_score, B * N_F0));
-    CKC(dmalloc(&h->d_best_h0, B * N_F0));
+    CKC(dmalloc(&h->d_best_score, B * N_F0 * SY_HS));
+    CKC(dmalloc(&h->d_best_h0, B * N_F0 * SY_HS));
     CKC(dmalloc(&h->d_f0, N)); CKC(dmalloc(&h->d_h0, N)); CKC(dmalloc(&h->d_score, N)); CKC(dmalloc(&h->d_ncand, B));
     CKC(dmalloc(&h->d_cycle_of, N));
     CKC(dmalloc(&h->d_status, N)); CKC(dmalloc(&h->d_llr_grid, N * 174)); CKC(dmalloc(&h->d_grid_sd, N)); CKC(dmalloc(&h->d_grid_snr, N));
@@ -356,10 +356,10 @@ static int launch_spectrogram(ft8_handle* h, const void* d_audio, int dtype, int
 static int launch_sync(ft8_handle* h, const float* d_grid, int grid_rows, int B, int odd_even, int b0 = 0) {
     const int cycle_h0 = odd_even ? 375 : 0;
     const size_t K = h->cfg.max_cands;
-    k_sync_scores<<<dim3(N_F0 / SY_TF, B), SY_NT, SY_SMEM_BYTES, h->stream>>>(d_grid, grid_rows, cycle_h0, h->d_best_score + (size_t)b0 * N_F0,
-                                                                              h->d_best_h0 + (size_t)b0 * N_F0);
+    k_sync_scores<<<dim3(SY_HS * (N_F0 / SY_TF), B), SY_NT, SY_SMEM_BYTES, h->stream>>>(
+        d_grid, grid_rows, cycle_h0, h->d_best_score + (size_t)b0 * N_F0 * SY_HS, h->d_best_h0 + (size_t)b0 * N_F0 * SY_HS);
     CK(cudaGetLastError());
-    k_topk<<<B, 960, 0, h->stream>>>(h->d_best_score + (size_t)b0 * N_F0, h->d_best_h0 + (size_t)b0 * N_F0, h->cfg.sync_score_min,
+    k_topk<<<B, 960, 0, h->stream>>>(h->d_best_score + (size_t)b0 * N_F0 * SY_HS, h->d_best_h0 + (size_t)b0 * N_F0 * SY_HS, h->cfg.sync_score_min,
                                      h->cfg.max_cands, h->d_f0 + b0 * K, h->d_h0 + b0 * K, h->d_score + b0 * K, h->d_ncand + b0);
     CK(cudaGetLastError());
     return FT8_OK;
