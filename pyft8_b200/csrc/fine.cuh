@@ -12,10 +12,12 @@
 //
 // F2/F3 restate Candidate._get_llr_fine / _get_signal_grid_fine (receiver.py:140-206):
 // one CTA per candidate; 1000 bins around fb -> taper (upper edge taper is inverted in the reference and
-// is reproduced as is) -> 3200-point inverse FFT in shared memory (first pass gathers the band straight
-// from global memory; 2200 of its 3200 inputs are structurally zero) -> 32-sample symbol DFTs.
-// 8 time tweaks share one inverse FFT; 9 frequency tweaks need one each; the best one is kept in a second
-// shared buffer so the final 79x8 grid needs no recomputation.  Only the MIDDLE Costas block is scored.
+// is reproduced as is) -> 3200-point inverse FFT in shared memory (passes 5,5,8,16; the first pass gathers the band
+// straight from global memory, 2200 of its 3200 inputs are structurally zero) -> 32-sample symbol DFTs, four per warp.
+// The 8 time tweaks share one inverse FFT; the 9 frequency tweaks need one each (the ftweak = 0 one is the time-scan
+// transform).  Only the MIDDLE Costas block is scored, so for scoring the last FFT pass is evaluated on just the
+// 224-238 samples that block covers; the winner's operands are kept in a third shared buffer and get the full last
+// pass for the final 79x8 grid.  Scoring of transform e shares a barrier phase with the first pass of transform e+1.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

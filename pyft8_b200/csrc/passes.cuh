@@ -7,8 +7,9 @@
 //   k_pass234  ipass 2-4 gate (nsync > 6, sd > sd_min); GOOD91 x2; LDPC(35,5) x2; LDPC(90,20) x5 (+save) -> list_osd
 //   k_osd_items ipass 5-6 one warp per (candidate, OSD attempt): 5 AP'd llrs then the saved post-LDPC llrs
 //   k_osd_resolve        first successful attempt in reference order wins
-// All kernels are persistent grid-stride loops over a device-resident list/count, so the host never reads a
-// count back between passes (no sync; the sequence is CUDA-graph capturable).
+// All kernels are persistent: warps pull work from device-resident lists through atomic cursors (the cost per candidate
+// varies from nothing to 110 LDPC iterations), so the host never reads a count back between passes (no sync; the
+// sequence of launches is fixed and CUDA-graph capturable).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
