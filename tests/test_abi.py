@@ -57,3 +57,15 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "ft8_oracle" not in txt and "ref_harness" not in txt, f
+
+
+def test_header_compiles_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit including only include/ft8_b200.h links against the library."""
+    import subprocess
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.join(ROOT, "pyft8_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", libdir, "-l:libft8_b200.so",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
