@@ -24,7 +24,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "decoded 15-s FT8 cycles/sec"
 UNIT = "cycles/s"
-WORKLOAD = "cfg2_50sig"
+WORKLOAD = "cfg2_50sig"          # BASELINE configs[1]; --workload selects configs[0] / configs[3] shapes for extra data points
 # algorithmic bytes per unit (DESIGN.md "Roofline accounting"); int16 audio in
 ALG_BYTES = {
     "spectrogram": 360000 + 375 * 976 * 4,          # per cycle: audio once + grid once
@@ -173,7 +173,7 @@ def run_reference(args, dist, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "cycles_per_step": per_step, "signals_per_cycle": 50, "host": "cpu"},
+        "config": {"workload": WORKLOAD, "cycles_per_step": per_step, "signals_per_cycle": workload.CONFIGS[WORKLOAD][0], "host": "cpu"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "ldpc_codewords_per_sec": ldpc / args.steps,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
@@ -301,7 +301,8 @@ def run_gpu(args, dist, rank, local, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "cycles_per_gpu_per_step": B, "signals_per_cycle": 50, "snr_db": [-24, 10],
+        "config": {"workload": WORKLOAD, "cycles_per_gpu_per_step": B, "signals_per_cycle": workload.CONFIGS[WORKLOAD][0],
+                   "snr_db": list(workload.CONFIGS[WORKLOAD][1]),
                    "audio": "int16 12 kHz 15 s", "l2": "inputs_larger_than_l2 (%.2f GB per step per GPU)" % (B * 360000 / 1e9),
                    "parallelism": f"cycles sharded over {world} GPU(s), no collective"},
         "ldpc_codewords_per_sec": ldpc_rate,
@@ -315,6 +316,7 @@ def run_gpu(args, dist, rank, local, world):
 
 
 def main():
+    global WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -322,9 +324,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cycles", type=int, default=4096, help="cycles per GPU per step (BASELINE configs[1]: 4096)")
     ap.add_argument("--seed", type=int, default=2000)
+    ap.add_argument("--workload", default=WORKLOAD, choices=["cfg1_20sig", "cfg2_50sig", "cfg4_120sig"],
+                    help="cfg2_50sig is the headline configuration (BASELINE configs[1])")
     ap.add_argument("--ref-cycles-per-core", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    WORKLOAD = args.workload
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     dist, rank, local, world = _dist_init()
     try:
