@@ -123,6 +123,8 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int
             if (hb) { if (pw == 0) u0 |= pb; else if (pw == 1) u1 |= pb; else u2 |= pb; }
             if (lane == 0) s.piv_row[npiv] = (uint8_t)p;
             ++npiv;
+            // A column that is still a unit vector (an untouched systematic column) eliminates nothing: skip the update.
+            if ((m0 | m1 | m2) == 0) continue;
             // pw is warp-uniform: three copies of the update, each testing a fixed word
             if (pw == 0) {
 #pragma unroll
