@@ -15,7 +15,8 @@
 //   * T = G[:, :91] are the columns with original index < 91 wherever they sit;
 //     trial word bit c = parity(u & col_c) with u[row of pivot k] = hard[column of pivot k];
 //     flipping u at the row of pivot 90-i adds (row of T) = bit (row) of every col_c.
-// CRC-14 is linear, so each of the 1+S vectors carries its 14-bit syndrome and a trial's CRC test is an XOR.
+// CRC-14 is linear, so each of the 1+S vectors carries its 14-bit syndrome and a trial's CRC test is an XOR;
+// the 91-bit word of a trial is only assembled when that XOR is zero.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,7 +33,7 @@ constexpr int OSD_MAX_FLIPS = 91;
 
 struct OsdWarpScratch {
     uint8_t piv_row[96];             // pivot k -> row
-    uint32_t vec[OSD_MAX_FLIPS + 1][4];   // [0] = order-0 word, [1+i] = row of T for flip i; [..][3] = CRC syndrome
+    uint16_t syn[OSD_MAX_FLIPS + 1];      // CRC syndrome of [0] the order-0 word, [1+i] the row of T that flip i adds
 };
 
 // Returns trial index + 1 of the first accepted trial word (0 = none); bits = that word.
@@ -139,54 +140,70 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int
         }
     }
     __syncwarp();
-    // ---- 4. the 1+S vectors over the original columns 0..90, each with its CRC syndrome
-    // per slot: where its bit lands in the 91-bit word (one of three masks is non-zero; none for columns >= 91)
-    uint32_t om0[6], om1[6], om2[6];
+    // ---- 4. CRC syndromes of the 1+S vectors over the original columns 0..90 (vector 0 = order-0 word, vector 1+i = row
+    //      of T that flip i adds).  Only the 14-bit syndromes are needed to test a trial; the 91-bit words themselves are
+    //      built on demand (osd_word) for the rare trials whose syndrome is zero.
+    //      Each slot first fetches the syndrome contribution of its original column from the lanes' register table.
+    uint32_t slot_syn[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         const uint32_t c = orig[k];
-        const uint32_t bit = (c < 91) ? (1u << (c & 31)) : 0u;
-        om0[k] = (c < 32) ? bit : 0u;
-        om1[k] = (c >= 32 && c < 64) ? bit : 0u;
-        om2[k] = (c >= 64) ? bit : 0u;
+        const uint32_t a0 = __shfl_sync(0xffffffffu, ls.s0, c & 31);
+        const uint32_t a1 = __shfl_sync(0xffffffffu, ls.s1, c & 31);
+        const uint32_t a2 = __shfl_sync(0xffffffffu, ls.s2, c & 31);
+        slot_syn[k] = (c < 32) ? a0 : ((c < 64) ? a1 : ((c < 91) ? a2 : 0u));
     }
     const int nvec = 1 + S;
     for (int vi = 0; vi < nvec; ++vi) {
-        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        uint32_t syn = 0;
         if (vi == 0) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const uint32_t m = 0u - ((__popc(c0[k] & u0) + __popc(c1[k] & u1) + __popc(c2[k] & u2)) & 1u);
-                w0 |= om0[k] & m; w1 |= om1[k] & m; w2 |= om2[k] & m;
-            }
+            for (int k = 0; k < 6; ++k)
+                if ((__popc(c0[k] & u0) + __popc(c1[k] & u1) + __popc(c2[k] & u2)) & 1) syn ^= slot_syn[k];
         } else {
             const int prow = s.piv_row[90 - (vi - 1)];
-            const int sh = prow & 31;
+            const uint32_t pbit = 1u << (prow & 31);
             if (prow < 32) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) { const uint32_t m = 0u - ((c0[k] >> sh) & 1u); w0 |= om0[k] & m; w1 |= om1[k] & m; w2 |= om2[k] & m; }
+                for (int k = 0; k < 6; ++k) if (c0[k] & pbit) syn ^= slot_syn[k];
             } else if (prow < 64) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) { const uint32_t m = 0u - ((c1[k] >> sh) & 1u); w0 |= om0[k] & m; w1 |= om1[k] & m; w2 |= om2[k] & m; }
+                for (int k = 0; k < 6; ++k) if (c1[k] & pbit) syn ^= slot_syn[k];
             } else {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) { const uint32_t m = 0u - ((c2[k] >> sh) & 1u); w0 |= om0[k] & m; w1 |= om1[k] & m; w2 |= om2[k] & m; }
+                for (int k = 0; k < 6; ++k) if (c2[k] & pbit) syn ^= slot_syn[k];
             }
         }
-        w0 = __reduce_or_sync(0xffffffffu, w0);
-        w1 = __reduce_or_sync(0xffffffffu, w1);
-        w2 = __reduce_or_sync(0xffffffffu, w2);
-        const uint32_t syn = syndrome_warp(w0, w1, w2, lane, ls);
-        if (lane == 0) { s.vec[vi][0] = w0; s.vec[vi][1] = w1; s.vec[vi][2] = w2; s.vec[vi][3] = syn; }
+        syn = __reduce_xor_sync(0xffffffffu, syn);
+        if (lane == 0) s.syn[vi] = (uint16_t)syn;
     }
     __syncwarp();
+    // 91-bit word of vector vi (-1: none), XOR-accumulated into w0..w2; every lane gets the result
+    auto osd_word = [&](int vi, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+        if (vi < 0) return;
+        uint32_t x0 = 0, x1 = 0, x2 = 0;
+        const int prow = vi > 0 ? s.piv_row[90 - (vi - 1)] : 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const uint32_t c = orig[k];
+            if (c < 91) {
+                uint32_t b;
+                if (vi == 0) b = (__popc(c0[k] & u0) + __popc(c1[k] & u1) + __popc(c2[k] & u2)) & 1u;
+                else b = (((prow < 32) ? c0[k] : ((prow < 64) ? c1[k] : c2[k])) >> (prow & 31)) & 1u;
+                if (b) { const uint32_t bit = 1u << (c & 31); if (c < 32) x0 |= bit; else if (c < 64) x1 |= bit; else x2 |= bit; }
+            }
+        }
+        w0 ^= __reduce_or_sync(0xffffffffu, x0);
+        w1 ^= __reduce_or_sync(0xffffffffu, x1);
+        w2 ^= __reduce_or_sync(0xffffffffu, x2);
+    };
     // ---- 5. enumerate trials in the reference's order; first with payload != 0, CRC ok, valid payload
     //      trial 0: base; 1..S: single flips i = 0..S-1; then pairs (i, j), j < D, j < i, i-major.
     const int nsingle = S;
     int npair = 0;
     for (int i = 0; i < S; ++i) npair += min(i, D);
     const int ntrial = 1 + nsingle + npair;
-    const uint32_t bs = s.vec[0][3];
+    const uint32_t bs = s.syn[0];
     for (int base = 0; base < ntrial; base += 32) {
         const int tr = base + lane;
         bool pass = false;
@@ -201,8 +218,8 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int
                 fi = i; fj = q;
             }
             uint32_t syn = bs;
-            if (fi >= 0) syn ^= s.vec[1 + fi][3];
-            if (fj >= 0) syn ^= s.vec[1 + fj][3];
+            if (fi >= 0) syn ^= s.syn[1 + fi];
+            if (fj >= 0) syn ^= s.syn[1 + fj];
             pass = (syn == 0);
         }
         uint32_t ballot = __ballot_sync(0xffffffffu, pass);
@@ -210,20 +227,18 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int
             const int src = __ffs(ballot) - 1;
             ballot &= ballot - 1;
             const int sfi = __shfl_sync(0xffffffffu, fi, src), sfj = __shfl_sync(0xffffffffu, fj, src);
-            uint32_t w[3];
-#pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                w[x] = s.vec[0][x];
-                if (sfi >= 0) w[x] ^= s.vec[1 + sfi][x];
-                if (sfj >= 0) w[x] ^= s.vec[1 + sfj][x];
-            }
+            uint32_t w[3] = {0u, 0u, 0u};
+            osd_word(0, w[0], w[1], w[2]);
+            osd_word(sfi >= 0 ? 1 + sfi : -1, w[0], w[1], w[2]);
+            osd_word(sfj >= 0 ? 1 + sfj : -1, w[0], w[1], w[2]);
             if ((w[0] | w[1] | (w[2] & 0x1FFFu)) != 0 && payload_valid(w)) {
                 bits[0] = w[0]; bits[1] = w[1]; bits[2] = w[2];
                 return base + src + 1;
             }
         }
     }
-    bits[0] = s.vec[0][0]; bits[1] = s.vec[0][1]; bits[2] = s.vec[0][2];
+    bits[0] = bits[1] = bits[2] = 0u;
+    osd_word(0, bits[0], bits[1], bits[2]);           // nothing accepted: report the order-0 word
     return 0;
 }
 
