@@ -86,7 +86,7 @@ __device__ __forceinline__ void set_result(const CandState& cs, int slot, const 
 }
 
 // ipass 0.  grid: [B][grid_rows][976].  payload_db (optional): [N][58][8].
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
 k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows, int cycle_h0, float sd_min,
         float* __restrict__ payload_db, int llr_only, int32_t* __restrict__ list_fine, int32_t* __restrict__ count_fine,
         int32_t* __restrict__ next_slot, DevStats* __restrict__ stats) {
@@ -250,7 +250,7 @@ struct OsdSmem {
 };
 
 // ipass 5-6: item = 10 * list index + attempt.  attempts 0..4: AP pattern on the fine llr; 5..9: saved llr.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
 k_osd_items(CandState cs, const int32_t* __restrict__ list, const int32_t* __restrict__ count, int S, int D,
             int32_t* __restrict__ next_item, DevStats* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char pass_smem_raw[];
@@ -349,7 +349,7 @@ k_ldpc_batch(float* __restrict__ llr, int N, int max_ncheck0, int max_iters, int
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
 k_osd_batch(const float* __restrict__ llr, int N, int S, int D, int32_t* __restrict__ found, uint32_t* __restrict__ bits_out) {
     extern __shared__ __align__(16) unsigned char pass_smem_raw[];
     OsdSmem& sm = *reinterpret_cast<OsdSmem*>(pass_smem_raw);
