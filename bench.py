@@ -40,6 +40,12 @@ ALG_BYTES = {
 NCU_DRAM_BYTES_PER_CYCLE = {"spectrogram": (1480e6 + 5960e6) / 4096, "sync": (2330e6 + 27e6) / 4096, "fine": (2730e6 + 493e6) / 4096,
                             "pass0_ldpc5": (3540e6 + 592e6) / 4096, "osd": (541e6 + 25e6) / 4096,
                             "cycle_spectrum": (787e6 + 369e6 + 369e6 + 731e6) / 1024}
+# issue-slot / pipe utilisation of the same captures (percent of peak): what actually bounds the non-HBM stages
+NCU_PIPES = {"spectrogram": {"issue_active": 79.3, "fma_pipe": 48.7, "alu_pipe": 28.2},
+             "sync": {"issue_active": 48.4, "fma_pipe": 17.6, "alu_pipe": 26.0},
+             "fine": {"issue_active": 51.5, "fma_pipe": 33.3, "alu_pipe": 13.6},
+             "pass0_ldpc5": {"issue_active": 57.1, "fma_pipe": 22.0, "alu_pipe": 23.6},
+             "osd": {"issue_active": 67.2, "fma_pipe": 6.5, "alu_pipe": 84.1}}
 STAGES = ["all", "spectrogram", "sync", "cycle_spectrum", "pass0_ldpc5", "fine", "pass234_ldpc", "osd", "collect"]
 
 
@@ -282,7 +288,7 @@ def run_gpu(args, dist, rank, local, world):
             traffic = NCU_DRAM_BYTES_PER_CYCLE.get(name)
             stages.append({"kernel": name, "ms": round(float(stage_ms[i]), 4), "share": round(float(stage_ms[i] / stage_ms[0]), 4),
                            "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
-                           "traffic": int(traffic * B) if traffic else None})
+                           "traffic": int(traffic * B) if traffic else None, "ncu_pct_of_peak": NCU_PIPES.get(name)})
     dom = max(stages, key=lambda s: s["ms"])
     roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
