@@ -21,12 +21,29 @@ from pyft8_b200 import synth, _lib as L  # noqa: E402
 from pyft8_b200.engine import Engine, bits91_to_int  # noqa: E402
 
 
+def _oracle_ldpc(x):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ft8_oracle as o
+    z = x.copy()
+    st, n, b = o.ldpc_decode(z, 90, 20)
+    return st, n, z
+
+
+def _oracle_osd(x):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ft8_oracle as o
+    b = o.osd(x.copy())
+    return b if b else 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=1000000)
-    ap.add_argument("--check", type=int, default=200)
+    ap.add_argument("--check", type=int, default=200, help="LDPC vectors per Eb/N0 point re-decoded by the CPU oracle")
+    ap.add_argument("--check-osd", type=int, default=50, help="OSD vectors per point re-decoded by the CPU oracle")
     args = ap.parse_args()
-    import ft8_oracle as o
+    import multiprocessing as mp
+    pool = mp.get_context("spawn").Pool(os.cpu_count())
     eng = Engine(max_cycles=1)
     rng = np.random.default_rng(3)
     msgs = [synth.pack77(*synth.random_message(rng)) for _ in range(1024)]
@@ -56,16 +73,21 @@ def main():
         assert np.all(eng.crc14(bits[ok]) == 3)
         if len(resc):
             assert np.all(eng.crc14(ob[resc]) == 3)
-        # oracle spot check (decision-level identity)
-        mism = 0
-        for i in range(min(args.check, per)):
-            z = llr[i].copy()
-            s, n, b = o.ldpc_decode(z, 90, 20)
-            mism += (s != (st[i] if st[i] != L.LDPC_STALL else L.LDPC_FAIL)) or (n != ni[i])
+        # oracle check (decision-level identity; llr after the last update within 2e-3)
+        nchk = min(args.check, per)
+        ref = pool.map(_oracle_ldpc, [llr[i] for i in range(nchk)], chunksize=64)
+        mism = llr_bad = 0
+        for i, (s_, n_, z_) in enumerate(ref):
+            mism += (s_ != (st[i] if st[i] != L.LDPC_STALL else L.LDPC_FAIL)) or (n_ != ni[i])
+            llr_bad += not np.allclose(z_, x[i], rtol=2e-3, atol=2e-3, equal_nan=True)
+        nosd = min(args.check_osd, len(fail))
+        ref_osd = pool.map(_oracle_osd, [llr[fail[j]] for j in range(nosd)], chunksize=8)
+        osd_mism = sum((bits91_to_int(ob[j]) if found[j] else 0) != ref_osd[j] for j in range(nosd))
         points.append(dict(ebn0_db=e, n=per, bp_ok=float(ok.mean()), mean_its_ok=float(ni[ok].mean()) if ok.any() else None,
                            osd_fallback=float(len(fail) / per), osd_rescued=float(len(resc) / max(len(fail), 1)),
                            wrong_bp_in_sample=int(wrong_bp), wrong_osd_in_sample=int(wrong_osd), oracle_mismatch=int(mism),
-                           oracle_checked=min(args.check, per)))
+                           oracle_llr_out_of_tol=int(llr_bad), oracle_checked=nchk, oracle_osd_mismatch=int(osd_mism),
+                           oracle_osd_checked=nosd))
     out = dict(metric="LDPC codewords/sec", value=args.n / (t_ldpc / 1e3), unit="codewords/s", n=args.n,
                ldpc_kernel_ms=t_ldpc, osd_calls=n_osd_total, osd_kernel_ms=t_osd,
                osd_per_sec=n_osd_total / (t_osd / 1e3), config="BASELINE configs[2]: Eb/N0 0..4 dB, ldpc_decode(.,90,20) then osd_012",
