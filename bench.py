@@ -245,32 +245,24 @@ def run_gpu(args, dist, rank, local, world):
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
     n_decoded, n_emitted = stats["decoded"], stats["emitted"]
-    # ---- end to end: pinned host audio in, records out, every step.  Two engines (handles) on two host threads each take
-    # half of the batch, so one handle's PCIe copy overlaps the other's kernels (ctypes releases the GIL in the call).
-    eng.close()
-    half = (B + 1) // 2
-    engs = [Engine(device=local, max_cycles=half) for _ in range(2)]
-    parts = [host_np[:half], host_np[half:]]
-    e2e_rec = [None, None]
-
-    def work(i, k):
-        for _ in range(k):                      # each handle streams its half-batches back to back
-            e2e_rec[i] = engs[i].decode_cycles(parts[i])
-
+    # ---- end to end: pinned host audio in, records out, every step, through Engine.decode_cycles (C ABI, host buffers).
+    # Batches are streamed the way a skimmer would: each call names the next batch (ft8_decode_cycles_stream), whose PCIe
+    # copy then runs on a second CUDA stream underneath this batch's kernels.  Every step's H2D copy and record D2H are
+    # inside the timed region.
     def e2e_steps(k):
-        th = [threading.Thread(target=work, args=(i, k)) for i in range(2) if len(parts[i])]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
+        n_dec = 0
+        eng.prefetch(host_np)                                   # copy of step 0
+        for i in range(k):
+            r_i, _ = eng.decode_cycles(host_np, next_audio=host_np if i + 1 < k else None)
+            n_dec = len(r_i)
+        return n_dec
 
     e2e_steps(min(args.warmup, 2))
     barrier()
     t0 = time.perf_counter()
-    e2e_steps(args.steps)
+    n_e2e_decoded = e2e_steps(args.steps)
     barrier()
     ms_e2e = max_over_ranks(1e3 * (time.perf_counter() - t0))
-    n_e2e_decoded = sum(len(x[0]) for x in e2e_rec if x is not None)
     total_cycles = sum_over_ranks(B)
     value = total_cycles * args.steps / (ms_dev / 1e3)
     e2e = total_cycles * args.steps / (ms_e2e / 1e3)
@@ -315,7 +307,7 @@ def run_gpu(args, dist, rank, local, world):
         "decodes_per_cycle": n_decoded / B, "emitted_per_cycle": n_emitted / B,
         "work_per_step": {k: stats[k] for k in ("candidates", "stopped_sd", "fine_evals", "fine_pass", "ldpc_calls", "ldpc_iters", "osd_calls")},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 360000), "d2h_bytes_per_step": int(n_e2e_decoded * 64 + 4 * B + 96),
-                "ms_per_step": ms_e2e / args.steps, "api": "2 x Engine.decode_cycles(host int16) on 2 threads, half batch each"},
+                "ms_per_step": ms_e2e / args.steps, "api": "Engine.decode_cycles(pinned host int16, next_audio=...) -> ft8_decode_cycles_stream: one handle, next batch copied under the kernels"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_stages": stages, "cpu_baseline": cpu,
     }
     print(json.dumps(out), flush=True)

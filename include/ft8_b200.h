@@ -171,6 +171,19 @@ int ft8_crc14(ft8_handle* h, const uint32_t* bits91, int N, int32_t* flags, int 
 int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even,
                       ft8_record* rec, int rec_capacity, int32_t* n_rec, int mem);
 
+/* Optional double buffering for callers that stream batches from host memory: starts the host->device copy of the NEXT
+ * batch on a second stream and returns at once.  A later ft8_decode_cycles(..., FT8_MEM_HOST) with the same pointer, dtype
+ * and B consumes the prefetched copy instead of copying again, so the transfer of batch i+1 overlaps the kernels of batch
+ * i.  The host buffer must stay valid and unchanged until that call; pinned memory is needed for the copy to be
+ * asynchronous. */
+int ft8_prefetch_audio(ft8_handle* h, const void* audio_host, int audio_dtype, int B);
+
+/* Streaming form of ft8_decode_cycles for host audio: decodes `audio` (consuming its prefetched copy when there is one) and
+ * at the same time starts the copy of `next_audio_host` (same dtype and B; NULL = none), i.e. one call per batch with a
+ * one-batch look-ahead keeps the PCIe transfer entirely underneath the kernels. */
+int ft8_decode_cycles_stream(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even,
+                             ft8_record* rec, int rec_capacity, int32_t* n_rec, const void* next_audio_host);
+
 /* Workload generator on the device (restates transmitter.py:52-70 + the 8d mixing recipe):
  * sums n_sig GFSK signals per cycle and white Gaussian noise into int16 audio[B][180000] (device or host per mem).
  * symbols: uint8 [B][n_sig][79]; f_hz, dt_s, amp: float [B][n_sig]. */

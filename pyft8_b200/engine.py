@@ -174,15 +174,32 @@ class Engine:
         return flags
 
     # ---- whole path
-    def decode_cycles(self, audio, odd_even=0):
-        """audio [B,180000] int16/float32 -> (records structured array in emission order, n_rec[B])."""
+    def decode_cycles(self, audio, odd_even=0, next_audio=None):
+        """audio [B,180000] int16/float32 -> (records structured array in emission order, n_rec[B]).
+
+        Streaming: pass the following batch as `next_audio` (same shape/dtype, ideally pinned); its host->device copy runs
+        underneath this batch's kernels and the next call consumes it (ft8_decode_cycles_stream)."""
         a, dt = self._audio(audio)
         B = a.shape[0]
         cap = B * self.max_cands
         rec = np.zeros(cap, L.RECORD_DTYPE)
         n = np.zeros(B, np.int32)
-        self._check(self._lib.ft8_decode_cycles(self._h, _ptr(a), dt, B, int(odd_even), _ptr(rec), cap, _ptr(n), L.MEM_HOST))
+        if next_audio is None:
+            self._check(self._lib.ft8_decode_cycles(self._h, _ptr(a), dt, B, int(odd_even), _ptr(rec), cap, _ptr(n), L.MEM_HOST))
+        else:
+            nx, ndt = self._audio(next_audio)
+            if ndt != dt or nx.shape != a.shape:
+                raise ValueError("next_audio must have the dtype and shape of audio")
+            self._pf_ref = nx
+            self._check(self._lib.ft8_decode_cycles_stream(self._h, _ptr(a), dt, B, int(odd_even), _ptr(rec), cap, _ptr(n), _ptr(nx)))
         return rec[:int(n.sum())], n
+
+    def prefetch(self, audio):
+        """Start copying the NEXT batch (host array, ideally pinned) while the current one is being decoded; the following
+        decode_cycles(audio) with the same array consumes the copy (ft8_prefetch_audio)."""
+        a, dt = self._audio(audio)
+        self._pf_ref = a                               # keep the host buffer alive until it is consumed
+        self._check(self._lib.ft8_prefetch_audio(self._h, _ptr(a), dt, a.shape[0]))
 
     def decode_cycles_dev(self, audio_ptr, dtype, B, odd_even=0, rec=None, n=None):
         """Same, with audio already resident on this engine's device (raw pointer)."""

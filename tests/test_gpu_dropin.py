@@ -76,3 +76,33 @@ def test_receiver_live_surface_matches_reference(name, golden_cycles):
     out = rx.decode_cycles(audio, emit=False)[0]
     assert [" ".join(m["msg_tuple"]) for m in out] == list(g["msg_text"])
     assert [m["decode_notes"] for m in out] == list(g["msg_notes"])
+
+
+@pytest.mark.gpu
+def test_streaming_decode_equals_plain_decode():
+    """ft8_prefetch_audio / ft8_decode_cycles_stream: the look-ahead copy changes when bytes move, not what is decoded."""
+    import torch
+    from pyft8_b200.engine import Engine
+    from pyft8_b200 import workload
+    eng = Engine(0, max_cycles=96)
+    batches = []
+    for seed in (1, 2, 3):
+        prm = workload.make_params("cfg1_20sig", 3, seed=seed)
+        a = np.stack([workload.host_cycle(prm, i) for i in range(3)])
+        a = np.tile(a, (32, 1))[:96]                      # > 64 cycles: the chunked-copy path
+        t = torch.from_numpy(a).pin_memory()
+        batches.append(t.numpy())
+    plain = [eng.decode_cycles(b) for b in batches]
+    # explicit prefetch, then streamed calls naming the next batch
+    eng.prefetch(batches[0])
+    streamed = []
+    for i, b in enumerate(batches):
+        nxt = batches[i + 1] if i + 1 < len(batches) else None
+        streamed.append(eng.decode_cycles(b, next_audio=nxt))
+    # not prefetched first batch but with a look-ahead (cold start of a stream)
+    cold = [eng.decode_cycles(batches[0], next_audio=batches[1]), eng.decode_cycles(batches[1])]
+    for (r0, n0), (r1, n1) in list(zip(plain, streamed)) + list(zip(plain[:2], cold)):
+        assert np.array_equal(n0, n1)
+        assert r0.tobytes() == r1.tobytes()
+    assert sum(int(n.sum()) for _, n in plain) > 0
+    eng.close()
