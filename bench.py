@@ -250,19 +250,26 @@ def run_gpu(args, dist, rank, local, world):
     # copy then runs on a second CUDA stream underneath this batch's kernels.  Every step's H2D copy and record D2H are
     # inside the timed region.
     def e2e_steps(k):
-        n_dec = 0
+        r_i = None
         eng.prefetch(host_np)                                   # copy of step 0
         for i in range(k):
             r_i, _ = eng.decode_cycles(host_np, next_audio=host_np if i + 1 < k else None)
-            n_dec = len(r_i)
-        return n_dec
+        return r_i
 
     e2e_steps(min(args.warmup, 2))
     barrier()
     t0 = time.perf_counter()
-    n_e2e_decoded = e2e_steps(args.steps)
+    rec_last = e2e_steps(args.steps)
     barrier()
     ms_e2e = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    n_e2e_decoded = len(rec_last)
+    # host text formatting of one step's records (outside every timed region): vectorised unpack + de-dup
+    from pyft8_b200.receiver import format_records
+    format_records(rec_last[:1000])
+    t0 = time.perf_counter()
+    mb = format_records(rec_last)
+    host_text = {"records_per_sec": len(rec_last) / max(time.perf_counter() - t0, 1e-9), "records": int(len(rec_last)),
+                 "messages": int(len(mb)), "note": "format_records on one step's records, one host thread, not in any timed region"}
     total_cycles = sum_over_ranks(B)
     value = total_cycles * args.steps / (ms_dev / 1e3)
     e2e = total_cycles * args.steps / (ms_e2e / 1e3)
@@ -308,7 +315,7 @@ def run_gpu(args, dist, rank, local, world):
         "work_per_step": {k: stats[k] for k in ("candidates", "stopped_sd", "fine_evals", "fine_pass", "ldpc_calls", "ldpc_iters", "osd_calls")},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 360000), "d2h_bytes_per_step": int(n_e2e_decoded * 64 + 4 * B + 96),
                 "ms_per_step": ms_e2e / args.steps, "api": "Engine.decode_cycles(pinned host int16, next_audio=...) -> ft8_decode_cycles_stream: one handle, next batch copied under the kernels"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_stages": stages, "cpu_baseline": cpu,
+        "host_text": host_text, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_stages": stages, "cpu_baseline": cpu,
     }
     print(json.dumps(out), flush=True)
 

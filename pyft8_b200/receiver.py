@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib as L
 from .engine import Engine, bits91_to_int
-from .messages import unpack, unpack_many
+from .messages import unpack, unpack_many, unpack_words
 from .time_utils import TimeUtils
 from . import decoders
 
@@ -274,6 +274,66 @@ def record_to_message(r, cyclestart_string="", band=None, odd_even=0, now=0.0, m
             "decode_notes": notes + tweaks, "bits77": bits91_to_int(r["bits91"]) >> 14, "cycle": int(r["cycle"])}
 
 
+_SRC = np.array(["grid", "fine"], object)
+_AP = np.array(L.AP_NAMES, object)
+_METHOD = np.array(L.METHOD_NAMES, object)
+
+
+def format_records(rec, cyclestart_strings=None):
+    """ft8_record array -> columnar decode list: numpy columns for everything numeric, message
+    tuples from messages.unpack_words (hash history kept, record order = emission order), text de-dup per cycle like
+    receiver.py:53-55.  Strings other than the message text are built only by MessageBatch.lines()/dicts()."""
+    msgs = np.empty(len(rec), object)
+    msgs[:] = unpack_words(rec["bits91"])
+    keep = np.array([m is not None for m in msgs.tolist()], bool)
+    text = np.array([" ".join(m) if m is not None else "" for m in msgs.tolist()], object)
+    cyc = rec["cycle"].astype(np.int64)
+    if keep.any():                                      # first record of every (cycle, text) wins
+        ki = np.flatnonzero(keep)
+        _, inv = np.unique(text[ki].astype(str), return_inverse=True)
+        key = cyc[ki] * (int(inv.max()) + 1) + inv
+        _, first = np.unique(key, return_index=True)
+        keep[:] = False
+        keep[ki[first]] = True
+    fine = rec["ipass"] >= 2
+    # python-float origin arithmetic of the reference (receiver.py:168-169, 350-351), in float64 like CPython
+    tsec = rec["h0_idx"].astype(np.float64) / 25.0 + np.where(fine, rec["ttweak"].astype(np.float64) / 200, 0.0)
+    fhz = 3.125 * rec["f0_idx"].astype(np.float64) + np.where(fine, rec["ftweak"].astype(np.float64) / 16, 0.0)
+    return MessageBatch(rec, msgs, text, keep, cyc, tsec, fhz, cyclestart_strings)
+
+
+class MessageBatch:
+    """Columnar view of one decoded batch; rows flagged by .keep are what the reference would have emitted."""
+
+    def __init__(self, rec, msgs, text, keep, cycle, tsec, fhz, cyclestart_strings):
+        self.rec, self.msg_tuple, self.text, self.keep, self.cycle = rec, msgs, text, keep, cycle
+        self.tsec, self.fHz, self.snr = tsec, fhz, rec["snr"].astype(np.int64)
+        self.cyclestart_strings = cyclestart_strings
+
+    def __len__(self):
+        return int(self.keep.sum())
+
+    def per_cycle_counts(self, n_cycles):
+        return np.bincount(self.cycle[self.keep], minlength=n_cycles)
+
+    def notes(self, idx):
+        """decode_notes strings (receiver.py:121-133 naming + tweaks) of the given rows."""
+        r = self.rec[idx]
+        src = _SRC[(r["ipass"] != 0).astype(np.int64)]
+        tw = ["t:+00 f:+00" if p < 2 else " t:%+03d f:%+03d" % (t, f)
+              for p, t, f in zip(r["ipass"].tolist(), r["ttweak"].tolist(), r["ftweak"].tolist())]
+        return [f"{a}_{b}_{c}{d}" for a, b, c, d in
+                zip(src.tolist(), _AP[r["ap"]].tolist(), _METHOD[r["method"]].tolist(), tw)]
+
+    def lines(self):
+        """ALL.TXT-style lines (receiver.py:63) of the kept rows, in emission order."""
+        i = np.flatnonzero(self.keep)
+        cs = self.cyclestart_strings
+        css = [cs[c] for c in self.cycle[i].tolist()] if cs else [""] * len(i)
+        return [f"{c} {s:+03d} {t - 0.6:4.1f} {f:4.0f} ~ {x}" for c, s, t, f, x in
+                zip(css, self.snr[i].tolist(), self.tsec[i].tolist(), self.fHz[i].tolist(), self.text[i].tolist())]
+
+
 class Receiver:
     def __init__(self, input_device_keywords, on_message, sync_score_min=85, max_cands=200, search_freq_range=[100, 3000],
                  search_time_range=[-2.5 + 0.5, 2.5 + 0.5], verbose=False, engine=None, clock=None, start_thread=False,
@@ -374,7 +434,7 @@ class Receiver:
         rec, n = self._batch_engine.decode_cycles(a, odd_even)
         out = [[] for _ in range(B)]
         seen = [set() for _ in range(B)]
-        texts = unpack_many(records_bits77(rec))          # in record (= emission) order: same hash history as the reference
+        texts = unpack_words(rec["bits91"])               # in record (= emission) order: same hash history as the reference
         for r, txt in zip(rec, texts):
             cyc = int(r["cycle"])
             cs = cyclestart_strings[cyc] if cyclestart_strings else ""
@@ -389,6 +449,22 @@ class Receiver:
             if emit and self.on_message:
                 self.on_message(m)
         return out
+
+
+    def decode_cycles_columnar(self, audio, odd_even=0, cyclestart_strings=None, next_audio=None):
+        """Skimmer-scale form of decode_cycles: returns a MessageBatch (numpy columns + lazily built strings) instead of
+        one dict per message; `next_audio` streams the following batch's copy under this batch's kernels."""
+        a = np.ascontiguousarray(audio)
+        if a.ndim == 1:
+            a = a[None]
+        B = a.shape[0]
+        if self._batch_engine is None or self._batch_engine.max_cycles < B:
+            if self._batch_engine is not None:
+                self._batch_engine.close()
+            self._batch_engine = Engine(device=self._device, max_cycles=B, max_cands=self.max_cands,
+                                        sync_score_min=self.sync_score_min)
+        rec, _ = self._batch_engine.decode_cycles(a, odd_even, next_audio=next_audio)
+        return format_records(rec, cyclestart_strings)
 
 
 def decode_cycles(audio, odd_even=0, device=0, **kw):

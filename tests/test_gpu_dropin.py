@@ -76,6 +76,13 @@ def test_receiver_live_surface_matches_reference(name, golden_cycles):
     out = rx.decode_cycles(audio, emit=False)[0]
     assert [" ".join(m["msg_tuple"]) for m in out] == list(g["msg_text"])
     assert [m["decode_notes"] for m in out] == list(g["msg_notes"])
+    # ... and so does the columnar (vectorised host formatting) form
+    messages.call_hashes.clear()
+    mb = rx.decode_cycles_columnar(audio, cyclestart_strings=["CS"])
+    kept = np.flatnonzero(mb.keep)
+    assert mb.text[kept].tolist() == list(g["msg_text"])
+    assert mb.notes(kept) == list(g["msg_notes"])
+    assert mb.lines() == [m["all_txt_format"].replace(m["cyclestart_string"], "CS", 1) if m["cyclestart_string"] else "CS" + m["all_txt_format"] for m in out]
 
 
 @pytest.mark.gpu

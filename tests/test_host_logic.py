@@ -127,7 +127,7 @@ def test_unpack_many_equals_sequential_unpack_with_hash_history():
     g1 = synth.pack77("CQ", "G1OJS", "IO90")
     seq = [hashed, pool[3], g1, hashed, pool[3], 0, 5, pool[7], g1, hashed] + [pool[i] for i in rng.integers(0, 64, 500)]
     messages.call_hashes.clear()
-    messages._TEXT_CACHE.clear()
+    messages._CALL_CACHE.clear()
     want = [messages.unpack(b) for b in seq]
     assert want[0] == ("<...>", "EA6VQ", "RR73") and want[3] == ("<G1OJS>", "EA6VQ", "RR73")      # history matters
     messages.call_hashes.clear()
@@ -146,3 +146,72 @@ def test_records_bits77_vectorised():
         rec["bits91"][i] = int_to_bits91(v)
     assert records_bits77(rec) == [v >> 14 for v in vals]
     assert records_bits77(rec[:0]) == []
+
+
+def _words_from_bits77(vals):
+    w = np.zeros((len(vals), 3), np.uint32)
+    for i, b in enumerate(vals):
+        v = int(format(int(b), "077b")[::-1], 2)
+        w[i] = (v & 0xFFFFFFFF, (v >> 32) & 0xFFFFFFFF, v >> 64)
+    return w
+
+
+def test_unpack_words_mixed_stream_equals_sequential_unpack():
+    """Vectorised batch unpack: same tuples and same hash-table end state as calling unpack() one by
+    one, on a stream mixing valid standard messages, random bits, hashed-call fields, type-4 messages and repeats."""
+    import copy
+    from pyft8_b200 import messages, synth
+    rng = np.random.default_rng(11)
+    pay = []
+    for _ in range(3000):
+        r = rng.random()
+        if r < 0.6:
+            pay.append(synth.pack77(*synth.random_message(rng)))
+        elif r < 0.8:
+            pay.append(int.from_bytes(rng.bytes(10), "big") >> 3)
+        elif r < 0.9:
+            b = synth.pack77(*synth.random_message(rng))
+            n28 = messages.NTOKENS + int(rng.integers(0, messages.MAX22 - 1))
+            sh = 49 if rng.random() < 0.5 else 20
+            pay.append((b & ~(((1 << 28) - 1) << sh)) | (n28 << sh))
+        else:
+            pay.append(((int.from_bytes(rng.bytes(10), "big") >> 3) & ~7) | 4)
+    pay += pay[:1000] + [0]
+    messages.call_hashes.clear(); messages.hashes_for_calls.clear()
+    want = [messages.unpack(b) for b in pay]
+    ch, hc = dict(messages.call_hashes), copy.deepcopy(messages.hashes_for_calls)
+    messages.call_hashes.clear(); messages.hashes_for_calls.clear()
+    got = messages.unpack_words(_words_from_bits77(pay))
+    assert got == want
+    assert messages.call_hashes == ch and messages.hashes_for_calls == hc
+    assert sum(m is not None for m in want) > 1500
+    assert messages.unpack_words(np.zeros((0, 3), np.uint32)) == []
+
+
+def test_format_records_matches_record_to_message():
+    from pyft8_b200 import messages, synth, _lib as L
+    from pyft8_b200.receiver import format_records, record_to_message
+    rng = np.random.default_rng(3)
+    vals = [synth.pack77(*synth.random_message(rng)) for _ in range(40)]
+    vals += vals[:5]                                       # same text twice in one cycle -> dropped; in another cycle -> kept
+    rec = np.zeros(len(vals), L.RECORD_DTYPE)
+    rec["bits91"] = _words_from_bits77(vals)
+    rec["cycle"] = np.r_[np.repeat(np.arange(4), 10), [0, 0, 3, 3, 3]]
+    rec["ipass"] = rng.integers(0, 7, len(vals))
+    rec["ap"] = rng.integers(0, 5, len(vals))
+    rec["method"] = rng.integers(0, 5, len(vals))
+    rec["h0_idx"] = rng.integers(-37, 87, len(vals))
+    rec["f0_idx"] = rng.integers(32, 960, len(vals))
+    rec["ttweak"] = rng.choice(np.arange(-8, 8, 2), len(vals))
+    rec["ftweak"] = rng.choice(np.arange(-32, 33, 8), len(vals))
+    rec["snr"] = rng.integers(-24, 25, len(vals))
+    cs = ["c%d" % i for i in range(4)]
+    mb = format_records(rec, cs)
+    assert mb.keep.tolist() == [True] * 40 + [False, False, True, True, True]
+    kept = np.flatnonzero(mb.keep)
+    dicts = [record_to_message(rec[i], cs[int(rec[i]["cycle"])]) for i in kept]
+    assert mb.lines() == [d["all_txt_format"] for d in dicts]
+    assert [mb.tsec[i] for i in kept] == [d["tsec"] for d in dicts]
+    assert [mb.fHz[i] for i in kept] == [d["fHz"] for d in dicts]
+    assert mb.notes(kept) == [d["decode_notes"] for d in dicts]
+    assert mb.per_cycle_counts(4).tolist() == [10, 10, 10, 13]
