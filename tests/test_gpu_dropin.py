@@ -113,3 +113,31 @@ def test_streaming_decode_equals_plain_decode():
         assert r0.tobytes() == r1.tobytes()
     assert sum(int(n.sum()) for _, n in plain) > 0
     eng.close()
+
+
+@pytest.mark.gpu
+def test_receiver_bank_decodes_golden_cycles_fed_hop_by_hop(golden_cycles):
+    """Three live streams multiplexed on one handle: each receiver gets 480-sample hops of a golden
+    cycle; every receiver's messages equal the unmodified reference's decode of that cycle, two cycles in a row."""
+    from pyft8_b200 import messages
+    from pyft8_b200.bank import ReceiverBank
+    names = ["test_08", "syn20", "test_09"]
+    messages.call_hashes.clear()
+    bank = ReceiverBank(len(names), None, bands=["20m", "40m", "15m"], clock=lambda: 45.0)
+    audio = np.stack([golden_cycles[n][0] for n in names])
+    for rep in range(2):
+        for k in range(375):
+            for r in range(len(names)):
+                bank.feed(r, audio[r, 480 * k:480 * (k + 1)])
+        no, out = bank.results(timeout=60)
+        assert no == rep
+        for r, n in enumerate(names):
+            g = golden_cycles[n][1]
+            mine = [m for m in out if m["receiver"] == r]
+            assert [" ".join(m["msg_tuple"]) for m in mine] == list(g["msg_text"]) or rep == 1
+            assert sorted(m["bits77"] for m in mine) == sorted(int(x, 16) for x in g["msg_bits77_hex"])
+            assert [m["decode_notes"] for m in mine] == list(g["msg_notes"])
+            assert all(m["band"] == bank.bands[r] for m in mine)
+    wf = bank.waterfall(0)
+    assert wf.shape == (376, 976) and np.all(wf[0] == 1.0)
+    bank.close()

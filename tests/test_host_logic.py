@@ -4,6 +4,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from conftest import ROOT, load_golden
 from pyft8_b200 import messages, synth
@@ -215,3 +216,47 @@ def test_format_records_matches_record_to_message():
     assert [mb.fHz[i] for i in kept] == [d["fHz"] for d in dicts]
     assert mb.notes(kept) == [d["decode_notes"] for d in dicts]
     assert mb.per_cycle_counts(4).tolist() == [10, 10, 10, 13]
+
+
+def test_receiver_bank_buffers_and_hands_over_whole_cycles():
+    """ReceiverBank host logic with a stub decoder: ragged per-receiver feeding, spill into the next
+    cycle, double buffering, message routing per receiver."""
+    from pyft8_b200 import synth, _lib as L
+    from pyft8_b200.bank import ReceiverBank, CYCLE_SAMPLES
+    seen = []
+
+    def stub(audio):
+        seen.append(audio.copy())
+        rec = np.zeros(audio.shape[0], L.RECORD_DTYPE)     # one message per receiver, call chosen by the first sample
+        for r in range(audio.shape[0]):
+            rec[r]["bits91"] = _words_from_bits77([synth.pack77("CQ", "K1ABC" if audio[r, 0] % 2 else "G1OJS", "IO90")])[0]
+            rec[r]["cycle"] = r
+        return rec
+    msgs = []
+    bank = ReceiverBank(3, msgs.append, bands=["20m", "40m", None], decoder=stub, clock=lambda: 45.0)
+    rng = np.random.default_rng(0)
+    stream = rng.integers(-3000, 3000, (3, 2 * CYCLE_SAMPLES + 1000)).astype(np.int16)
+    sent = [0, 0, 0]
+    closed = 0
+    while min(sent) < stream.shape[1]:
+        r = int(np.argmin(sent))                           # keep the receivers within one block of each other
+        k = int(rng.integers(100, 5000))
+        closed += bank.feed(r, stream[r, sent[r]:sent[r] + k])
+        sent[r] = min(sent[r] + k, stream.shape[1])
+    assert closed == 2
+    got = [bank.results(timeout=10) for _ in range(2)]
+    assert [g[0] for g in got] == [0, 1]
+    assert np.array_equal(seen[0], stream[:, :CYCLE_SAMPLES])
+    assert np.array_equal(seen[1], stream[:, CYCLE_SAMPLES:2 * CYCLE_SAMPLES])
+    assert bank._pos.tolist() == [1000, 1000, 1000]
+    assert [m["receiver"] for m in got[0][1]] == [0, 1, 2] and [m["band"] for m in got[0][1]] == ["20m", "40m", None]
+    want = ["CQ K1ABC IO90" if stream[r, 0] % 2 else "CQ G1OJS IO90" for r in range(3)]
+    assert [" ".join(m["msg_tuple"]) for m in got[0][1]] == want
+    assert len(msgs) == 6
+    with pytest.raises(TypeError):
+        bank.feed(0, np.zeros(10, np.float32))
+    assert bank.feed_all(np.zeros((3, CYCLE_SAMPLES - 1000), np.int16)) == 1
+    bank.results(timeout=10)
+    with pytest.raises(BufferError):                       # one receiver running two cycles ahead of the others
+        bank.feed(1, np.zeros(2 * CYCLE_SAMPLES + 1, np.int16))
+    bank.close()
