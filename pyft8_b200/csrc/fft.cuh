@@ -1,4 +1,4 @@
-// fft.cuh -- shared-memory Stockham FFT building blocks (radix 2/3/4/5/8/16), fp32 complex.
+// fft.cuh -- shared-memory Stockham FFT building blocks (radix 2/3/4/5/8/15/16), fp32 complex, packed f32x2 arithmetic.
 //
 // Every transform on the FT8 receive path has a length with factors 2, 3 and 5 only
 // (3840 = 2*1920 real, 192000 = 2*(375*256) real, 3200, 32), so the library
@@ -16,22 +16,80 @@
 
 namespace ft8 {
 
+// ---- complex helpers.  Two implementations with the SAME rounding sequence (products rounded once, fma exactly where
+// the formulas quoted below have fmaf), so they produce bit-identical results:
+//   * scalar FFMA/FADD/FMUL (default);
+//   * -DFT8_PACKED_F32X2: Blackwell packed fp32x2 (FFMA2 / FADD2 / FMUL2, one instruction per complex number; ptxas
+//     folds operand swaps, scalar broadcasts and per-half sign changes into modifiers such as R.F32x2.LO_HI.NP / R.F32,
+//     so a complex multiply is 2 instructions and a multiply by +-i inside an add is free).
+// Measured on B200 (tools/micro/ffma2_bench.cu, tools/variant_bench.py): FFMA2 sustains the FFMA flop rate with half the
+// issue slots (72 Tflop/s either way); the packed build has 21 % fewer instructions in k_spectrogram (9.08 -> 8.65 ms)
+// but k_fine, which waits on barriers and the shared-memory pipe rather than on issue slots, gets 1.2 % slower
+// (71.5 -> 72.4 ms), so the whole step does not gain and the default stays scalar.
+#ifdef FT8_PACKED_F32X2
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ u64 P(float2 a) { return pk(a.x, a.y); }
+__device__ __forceinline__ float2 U(u64 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 bc(float s) { return pk(s, s); }                      // scalar broadcast
+__device__ __forceinline__ u64 sw(float2 a) { return pk(a.y, a.x); }                // swapped halves
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return U(fma2(bc(a.x), P(b), mul2(pk(b.y, -b.x), bc(-a.y)))); }
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return U(fma2(P(a), bc(b.x), mul2(pk(a.y, -a.x), bc(b.y)))); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return U(add2(P(a), P(b))); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return U(sub2(P(a), P(b))); }
+__device__ __forceinline__ float2 caxpy(float s, float2 a, float2 c) { return U(fma2(bc(s), P(a), P(c))); }
+__device__ __forceinline__ float2 cscale(float s, float2 a) { return U(mul2(bc(s), P(a))); }
+__device__ __forceinline__ float2 cmul_elem(float2 a, float2 b) { return U(mul2(P(a), P(b))); }
+__device__ __forceinline__ float2 cfma_elem(float2 a, float sx, float sy, float2 c) { return U(fma2(P(a), pk(sx, sy), P(c))); }
+template <bool INV> __device__ __forceinline__ float2 addrot(float2 d, float2 x, float s = 1.0f) {
+    return U(fma2(sw(x), INV ? pk(-s, s) : pk(s, -s), P(d)));
+}
+template <bool INV> __device__ __forceinline__ float2 subrot(float2 d, float2 x, float s = 1.0f) {
+    return U(fma2(sw(x), INV ? pk(s, -s) : pk(-s, s), P(d)));
+}
+// acc + v*w with acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x)), acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y))
+__device__ __forceinline__ float2 cmac(float2 acc, float2 v, float2 w) {
+    return U(fma2(bc(v.x), P(w), fma2(pk(w.y, -w.x), bc(-v.y), P(acc))));
+}
+#else
+// (fmaf(a.x, b.x, -a.y*b.y), fmaf(a.x, b.y, a.y*b.x))
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
-__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
+// a * conj(b) = (fmaf(a.x, b.x, a.y*b.y), fmaf(a.y, b.x, -a.x*b.y))
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// s*a + c per component, s*a, a*b per component, a*(sx,sy) + c per component
+__device__ __forceinline__ float2 caxpy(float s, float2 a, float2 c) { return make_float2(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y)); }
+__device__ __forceinline__ float2 cscale(float s, float2 a) { return make_float2(s * a.x, s * a.y); }
+__device__ __forceinline__ float2 cmul_elem(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 cfma_elem(float2 a, float sx, float sy, float2 c) { return make_float2(fmaf(a.x, sx, c.x), fmaf(a.y, sy, c.y)); }
+// d + s*rot90<INV>(x) and d - s*rot90<INV>(x)   (rot90 = times +i for INV, -i otherwise; s = 1: a plain add/sub)
+template <bool INV> __device__ __forceinline__ float2 addrot(float2 d, float2 x, float s = 1.0f) {
+    return INV ? make_float2(fmaf(x.y, -s, d.x), fmaf(x.x, s, d.y)) : make_float2(fmaf(x.y, s, d.x), fmaf(x.x, -s, d.y));
+}
+template <bool INV> __device__ __forceinline__ float2 subrot(float2 d, float2 x, float s = 1.0f) {
+    return INV ? make_float2(fmaf(x.y, s, d.x), fmaf(x.x, -s, d.y)) : make_float2(fmaf(x.y, -s, d.x), fmaf(x.x, s, d.y));
+}
+__device__ __forceinline__ float2 cmac(float2 acc, float2 v, float2 w) {
+    return make_float2(fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x)), fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y)));
+}
+#endif
 // multiply by -i (forward) or +i (inverse)
 template <bool INV> __device__ __forceinline__ float2 rot90(float2 a) {
     return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
 
-template <int R, bool INV> struct Dft;
+template <int R, bool INV, bool ROT2 = false> struct Dft;
 
-template <bool INV> struct Dft<2, INV> {
+template <bool INV> struct Dft<2, INV, false> {
     static __device__ __forceinline__ void run(float2* a) {
         float2 t = a[0];
         a[0] = cadd(t, a[1]);
@@ -39,49 +97,51 @@ template <bool INV> struct Dft<2, INV> {
     }
 };
 
-template <bool INV> struct Dft<3, INV> {
+template <bool INV> struct Dft<3, INV, false> {
     static __device__ __forceinline__ void run(float2* a) {
         const float s = 0.86602540378443864676f;
-        float2 t = cadd(a[1], a[2]);
-        float2 d = rot90<INV>(csub(a[1], a[2]));       // -/+ i*(a1-a2)
-        float2 m = make_float2(fmaf(-0.5f, t.x, a[0].x), fmaf(-0.5f, t.y, a[0].y));
+        const float2 t = cadd(a[1], a[2]);
+        const float2 u = csub(a[1], a[2]);               // a1, a2 = m +- s*rot90(u)
+        const float2 m = caxpy(-0.5f, t, a[0]);
         a[0] = cadd(a[0], t);
-        a[1] = make_float2(fmaf(s, d.x, m.x), fmaf(s, d.y, m.y));
-        a[2] = make_float2(fmaf(-s, d.x, m.x), fmaf(-s, d.y, m.y));
+        a[1] = addrot<INV>(m, u, s);
+        a[2] = subrot<INV>(m, u, s);
     }
 };
 
-template <bool INV> struct Dft<4, INV> {
+// ROT2: a[2] is still to be multiplied by -/+ i (folded into the first add/sub)
+template <bool INV, bool ROT2> struct Dft<4, INV, ROT2> {
     static __device__ __forceinline__ void run(float2* a) {
-        float2 s02 = cadd(a[0], a[2]), d02 = csub(a[0], a[2]);
-        float2 s13 = cadd(a[1], a[3]), d13 = rot90<INV>(csub(a[1], a[3]));
+        const float2 s02 = ROT2 ? addrot<INV>(a[0], a[2]) : cadd(a[0], a[2]);
+        const float2 d02 = ROT2 ? subrot<INV>(a[0], a[2]) : csub(a[0], a[2]);
+        const float2 s13 = cadd(a[1], a[3]), u = csub(a[1], a[3]);
         a[0] = cadd(s02, s13);
         a[2] = csub(s02, s13);
-        a[1] = cadd(d02, d13);
-        a[3] = csub(d02, d13);
+        a[1] = addrot<INV>(d02, u);
+        a[3] = subrot<INV>(d02, u);
     }
 };
 
-template <bool INV> struct Dft<5, INV> {
+template <bool INV> struct Dft<5, INV, false> {
     static __device__ __forceinline__ void run(float2* a) {
         const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
         const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-        float2 t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]);
-        float2 t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
-        float2 m1 = make_float2(fmaf(c1, t1.x, fmaf(c2, t2.x, a[0].x)), fmaf(c1, t1.y, fmaf(c2, t2.y, a[0].y)));
-        float2 m2 = make_float2(fmaf(c2, t1.x, fmaf(c1, t2.x, a[0].x)), fmaf(c2, t1.y, fmaf(c1, t2.y, a[0].y)));
-        float2 n1 = rot90<INV>(make_float2(fmaf(s1, t3.x, s2 * t4.x), fmaf(s1, t3.y, s2 * t4.y)));
-        float2 n2 = rot90<INV>(make_float2(fmaf(s2, t3.x, -s1 * t4.x), fmaf(s2, t3.y, -s1 * t4.y)));
+        const float2 t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]);
+        const float2 t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
+        const float2 m1 = caxpy(c1, t1, caxpy(c2, t2, a[0]));
+        const float2 m2 = caxpy(c2, t1, caxpy(c1, t2, a[0]));
+        const float2 u1 = caxpy(s1, t3, cscale(s2, t4));            // n1 = rot90(u1), n2 = rot90(u2)
+        const float2 u2 = caxpy(s2, t3, cscale(-s1, t4));
         a[0] = cadd(a[0], cadd(t1, t2));
-        a[1] = cadd(m1, n1);
-        a[4] = csub(m1, n1);
-        a[2] = cadd(m2, n2);
-        a[3] = csub(m2, n2);
+        a[1] = addrot<INV>(m1, u1);
+        a[4] = subrot<INV>(m1, u1);
+        a[2] = addrot<INV>(m2, u2);
+        a[3] = subrot<INV>(m2, u2);
     }
 };
 
 // 8 = 2 x 4 in registers: j = 4*j1 + j2, k = k1 + 2*k2
-template <bool INV> struct Dft<8, INV> {
+template <bool INV> struct Dft<8, INV, false> {
     static __device__ __forceinline__ void run(float2* a) {
         const float h = 0.70710678118654752440f;
         float2 c[2][4];
@@ -90,16 +150,15 @@ template <bool INV> struct Dft<8, INV> {
             c[0][j2] = cadd(a[j2], a[4 + j2]);
             c[1][j2] = csub(a[j2], a[4 + j2]);
         }
-        // twiddle w8^(j2*k1) on the k1 = 1 row
+        // twiddle w8^(j2*k1) on the k1 = 1 row; c[1][2] (times -/+ i) is rotated inside the radix-4 step
         {
-            float2 v = c[1][1];   // * w8^1 = (1 -/+ i)/sqrt2
-            c[1][1] = INV ? make_float2(h * (v.x - v.y), h * (v.x + v.y)) : make_float2(h * (v.x + v.y), h * (v.y - v.x));
-            c[1][2] = rot90<INV>(c[1][2]);
-            v = c[1][3];          // * w8^3 = (-1 -/+ i)/sqrt2
-            c[1][3] = INV ? make_float2(-h * (v.x + v.y), h * (v.x - v.y)) : make_float2(h * (v.y - v.x), -h * (v.x + v.y));
+            float2 v = c[1][1];   // * w8^1 = (1 -/+ i)/sqrt2 :  INV (h(vx-vy), h(vx+vy)),  fwd (h(vx+vy), h(vy-vx))
+            c[1][1] = cscale(h, addrot<INV>(v, v));
+            v = c[1][3];          // * w8^3 = (-1 -/+ i)/sqrt2 : INV (-h(vx+vy), h(vx-vy)), fwd (h(vy-vx), -h(vx+vy))
+            c[1][3] = cscale(-h, subrot<INV>(v, v));
         }
-        Dft<4, INV>::run(c[0]);
-        Dft<4, INV>::run(c[1]);
+        Dft<4, INV, false>::run(c[0]);
+        Dft<4, INV, true>::run(c[1]);
 #pragma unroll
         for (int k2 = 0; k2 < 4; ++k2) {
             a[2 * k2] = c[0][k2];
@@ -109,28 +168,31 @@ template <bool INV> struct Dft<8, INV> {
 };
 
 // 16 = 4 x 4 in registers: j = 4*j1 + j2, k = k1 + 4*k2
-template <bool INV> struct Dft<16, INV> {
+template <bool INV> struct Dft<16, INV, false> {
     static __device__ __forceinline__ void run(float2* a) {
         const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
         float2 c[4][4];   // c[k1][j2]
 #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) {
             float2 t[4] = {a[j2], a[4 + j2], a[8 + j2], a[12 + j2]};
-            Dft<4, INV>::run(t);
+            Dft<4, INV, false>::run(t);
 #pragma unroll
             for (int k1 = 0; k1 < 4; ++k1) c[k1][j2] = t[k1];
         }
-        // twiddles w16^(j2*k1), k1,j2 in 1..3 : exponents 1,2,3 / 2,4,6 / 3,6,9
+        // twiddles w16^(j2*k1), k1,j2 in 1..3 : exponents 1,2,3 / 2,4,6 / 3,6,9  (w16^4 = -/+ i is folded into the radix-4 step)
         const float2 w1 = make_float2(c1, -s1), w2 = make_float2(h, -h), w3 = make_float2(s1, -c1);
         const float2 w6 = make_float2(-h, -h), w9 = make_float2(-c1, s1);
 #define FT8_TW(v, w) v = INV ? cmulc(v, w) : cmul(v, w)
         FT8_TW(c[1][1], w1); FT8_TW(c[1][2], w2); FT8_TW(c[1][3], w3);
-        FT8_TW(c[2][1], w2); c[2][2] = rot90<INV>(c[2][2]); FT8_TW(c[2][3], w6);
+        FT8_TW(c[2][1], w2); FT8_TW(c[2][3], w6);
         FT8_TW(c[3][1], w3); FT8_TW(c[3][2], w6); FT8_TW(c[3][3], w9);
 #undef FT8_TW
+        Dft<4, INV, false>::run(c[0]);
+        Dft<4, INV, false>::run(c[1]);
+        Dft<4, INV, true>::run(c[2]);
+        Dft<4, INV, false>::run(c[3]);
 #pragma unroll
         for (int k1 = 0; k1 < 4; ++k1) {
-            Dft<4, INV>::run(c[k1]);
 #pragma unroll
             for (int k2 = 0; k2 < 4; ++k2) a[k1 + 4 * k2] = c[k1][k2];
         }
@@ -138,7 +200,7 @@ template <bool INV> struct Dft<16, INV> {
 };
 
 // 15 = 3 x 5 in registers: j = 5*j1 + j2, k = k1 + 3*k2;  w15^(jk) = w3^(j1 k1) * w15^(j2 k1) * w5^(j2 k2)
-template <bool INV> struct Dft<15, INV> {
+template <bool INV> struct Dft<15, INV, false> {
     static __device__ __forceinline__ void run(float2* a) {
         float2 c[3][5];   // c[k1][j2]
 #pragma unroll

@@ -113,8 +113,9 @@ k_cs_rows(const float2* __restrict__ Y, float2* __restrict__ spec, int spec_stri
         const int k2m = (k1 == 0) ? ((CS_N2 - k2) & (CS_N2 - 1)) : (CS_N2 - 1 - k2);
         const float2 zk = rows[r][k2];
         const float2 zm = rows[CSR_G + r][k2m];
-        const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-        const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+        const float2 e = cscale(0.5f, cfma_elem(zm, 1.0f, -1.0f, zk));                       // (zk + conj(zm))/2
+        const float2 dz = cfma_elem(zm, -1.0f, 1.0f, zk);
+            const float2 o = make_float2(0.5f * dz.y, -0.5f * dz.x);       // -i/2 (zk - conj(zm))
         const float2 wo = cmul(o, __ldg(&W192000[k]));
         if (k <= kmax) out[k] = cadd(e, wo);
         const int km = CS_N - k;                            // mirrored output bin, conj(E - W O)
@@ -151,7 +152,7 @@ __device__ __forceinline__ void fine_pass1(float2* tmp, const float2* __restrict
             float2 b[5] = {a0, a0, a0, a0, a0};
             if (p < 210) {                                          // i = p + 640 in [640, 850)
                 float2 a1 = __ldg(&spec[fb + p + 640]);
-                if (p >= 110) { const float t = taper[p - 110]; a1.x *= t; a1.y *= t; }
+                if (p >= 110) a1 = cscale(taper[p - 110], a1);
                 const float2 w1 = make_float2(0.30901699437494742410f, 0.95105651629515357212f);
                 const float2 w2 = make_float2(-0.80901699437494742410f, 0.58778525229247312917f);
                 b[0] = cadd(a0, a1);
@@ -161,7 +162,7 @@ __device__ __forceinline__ void fine_pass1(float2* tmp, const float2* __restrict
                 b[4] = cadd(a0, cmulc(a1, w1));
             } else if (p >= 490) {                                  // i = p + 2560 in [3050, 3200)
                 float2 a4 = __ldg(&spec[fb + p - 640]);
-                if (p < 590) { const float t = taper[p - 490]; a4.x *= t; a4.y *= t; }
+                if (p < 590) a4 = cscale(taper[p - 490], a4);
                 const float2 w1 = make_float2(0.30901699437494742410f, 0.95105651629515357212f);
                 const float2 w2 = make_float2(-0.80901699437494742410f, 0.58778525229247312917f);
                 b[0] = cadd(a0, a4);
@@ -195,8 +196,7 @@ __device__ __forceinline__ void fine_pass4_window(const float2* x, float2* zwin,
         for (int j = 1; j < 16; ++j) {
             const float2 w = w16[(j * kk) & 15];
             const float2 v = x[q + 200 * j];
-            acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
-            acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
+            acc = cmac(acc, v, w);
         }
         zwin[tid] = acc;
     }

@@ -65,7 +65,7 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
             if (live && si >= 0) {                      // si is even: the pair never straddles the cycle start
                 const float2 w = __ldg(reinterpret_cast<const float2*>(hann + 2 * n));
                 const float2 v = load_sample_pair(x, si);
-                z = make_float2(v.x * w.x, v.y * w.y);
+                z = cmul_elem(v, w);
             }
             a[j] = z;
         }
@@ -81,8 +81,10 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
         for (int k = lt; k < GRID_COLS; k += SP_NT) {
             const float2 zk = buf[k];
             const float2 zm = buf[k == 0 ? 0 : 1920 - k];
-            const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-            const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));   // -i/2 * (zk - conj(zm))
+            // e = (zk + conj(zm))/2,  o = -i/2 * (zk - conj(zm)) = (0.5 (zk.y + zm.y), -0.5 (zk.x - zm.x))
+            const float2 e = cscale(0.5f, cfma_elem(zm, 1.0f, -1.0f, zk));
+            const float2 dz = cfma_elem(zm, -1.0f, 1.0f, zk);
+            const float2 o = make_float2(0.5f * dz.y, -0.5f * dz.x);
             const float2 w = __ldg(&W3840[k]);
             const float2 X = cadd(e, cmul(o, w));
             // 20*log10(|X| + 1e-12): for |X|^2 > 1e-8 the 1e-12 is below half an ulp of |X| and 20*log10|X| = 10*log10(|X|^2),

@@ -174,16 +174,25 @@ class Engine:
         return flags
 
     # ---- whole path
-    def decode_cycles(self, audio, odd_even=0, next_audio=None):
+    def decode_cycles(self, audio, odd_even=0, next_audio=None, rec=None, n=None):
         """audio [B,180000] int16/float32 -> (records structured array in emission order, n_rec[B]).
+
+        `rec` / `n`: optional caller-owned output arrays (RECORD_DTYPE[>= B*max_cands is always enough], int32[B]); pass
+        pinned ones to make the record copy-back a straight DMA.  The returned records are a view of `rec`.
 
         Streaming: pass the following batch as `next_audio` (same shape/dtype, ideally pinned); its host->device copy runs
         underneath this batch's kernels and the next call consumes it (ft8_decode_cycles_stream)."""
         a, dt = self._audio(audio)
         B = a.shape[0]
-        cap = B * self.max_cands
-        rec = np.zeros(cap, L.RECORD_DTYPE)
-        n = np.zeros(B, np.int32)
+        if rec is None:
+            rec = np.zeros(B * self.max_cands, L.RECORD_DTYPE)
+        elif rec.dtype != L.RECORD_DTYPE or not rec.flags.c_contiguous:
+            raise ValueError("rec must be a contiguous RECORD_DTYPE array")
+        if n is None:
+            n = np.zeros(B, np.int32)
+        elif n.dtype != np.int32 or len(n) < B or not n.flags.c_contiguous:
+            raise ValueError("n must be a contiguous int32 array of at least B entries")
+        cap = len(rec)
         if next_audio is None:
             self._check(self._lib.ft8_decode_cycles(self._h, _ptr(a), dt, B, int(odd_even), _ptr(rec), cap, _ptr(n), L.MEM_HOST))
         else:
