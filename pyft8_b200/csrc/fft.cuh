@@ -229,35 +229,52 @@ template <bool INV> struct Dft<15, INV, false> {
     }
 };
 
+// Index maps for shared-memory buffers: identity, or one padding element after every 16 (turns the stride-16 stores of a
+// radix-16 first pass, which would all hit one 8-byte bank, into stride 17).
+struct IdMap { static __device__ __forceinline__ int at(int i) { return i; } };
+struct Pad16Map { static __device__ __forceinline__ int at(int i) { return i + (i >> 4); } };
+
 // One Stockham pass for butterfly t (0 <= t < N/R).  x, y may be any addressable memory.
-// W is the length-N twiddle table (W[j] = exp(-2 pi i j / N)), read through the read-only path.
-template <int N, int R, int S> struct Pass {
+// PM selects how t maps to (p, q): false -> p = t / S, q = t % S (consecutive threads read consecutive elements);
+// true -> q = t / M, p = t % M: consecutive threads take consecutive p, so loads have stride S and stores stride R*S
+// elements -- conflict-free in shared memory when both are odd -- and the [k-1][p] twiddle reads are fully coalesced.
+template <int N, int R, int S, bool PM = false> struct Pass {
     static constexpr int M = N / (S * R);
-    static __device__ __forceinline__ void load(const float2* x, int t, float2* a) {
-        const int p = t / S, q = t - p * S;
-#pragma unroll
-        for (int j = 0; j < R; ++j) a[j] = x[q + S * (p + M * j)];
+    static __device__ __forceinline__ void decode(int t, int& p, int& q) {
+        if (PM) { q = t / M; p = t - q * M; } else { p = t / S; q = t - p * S; }
     }
-    template <bool INV>
+    template <class MapIn = IdMap>
+    static __device__ __forceinline__ void load(const float2* x, int t, float2* a) {
+        int p, q;
+        decode(t, p, q);
+#pragma unroll
+        for (int j = 0; j < R; ++j) a[j] = x[MapIn::at(q + S * (p + M * j))];
+    }
+    // TT = false: W is the plain length-N table, twiddle w_{N/S}^{pk} = W[p*k*S] (a gather whose stride grows with k: up
+    // to one 32-byte sector per lane).  TT = true: W is this pass's own table laid out [k-1][p] (pass_table() on the host,
+    // same values), so the lanes of a warp read consecutive entries -- the twiddle loads of a pass then cost 2-8 sectors
+    // per request instead of up to 32 on the L1/shared-memory data path that bounds the FFT kernels.
+    template <bool INV, bool TT = false, class MapOut = IdMap>
     static __device__ __forceinline__ void compute_store(float2* y, int t, float2* a, const float2* __restrict__ W) {
-        const int p = t / S, q = t - p * S;
+        int p, q;
+        decode(t, p, q);
         Dft<R, INV>::run(a);
-        y[q + S * (R * p)] = a[0];
+        y[MapOut::at(q + S * (R * p))] = a[0];
 #pragma unroll
         for (int k = 1; k < R; ++k) {
             float2 v = a[k];
             if (M > 1) {
-                float2 w = __ldg(&W[p * k * S]);
+                float2 w = __ldg(TT ? &W[(k - 1) * M + p] : &W[p * k * S]);
                 v = INV ? cmulc(v, w) : cmul(v, w);
             }
-            y[q + S * (R * p + k)] = v;
+            y[MapOut::at(q + S * (R * p + k))] = v;
         }
     }
 };
 
 // In-place pass over a shared-memory buffer by a group of NT threads (lt = thread index in the group):
 // all operands are read into registers, the group synchronises (sync functor), then results are written.
-template <int N, int R, int S, int NT, bool INV, class Sync>
+template <int N, int R, int S, int NT, bool INV, class Sync, bool TT = false>
 __device__ __forceinline__ void pass_inplace(float2* buf, int lt, const float2* __restrict__ W, Sync sync) {
     constexpr int NBF = N / R;
     constexpr int PER = (NBF + NT - 1) / NT;
@@ -271,7 +288,7 @@ __device__ __forceinline__ void pass_inplace(float2* buf, int lt, const float2* 
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         int t = lt + i * NT;
-        if (t < NBF) Pass<N, R, S>::template compute_store<INV>(buf, t, a[i], W);
+        if (t < NBF) Pass<N, R, S>::template compute_store<INV, TT>(buf, t, a[i], W);
     }
     sync();
 }
@@ -308,7 +325,8 @@ template <int NT, bool INV> __device__ __forceinline__ void fft32(float2* buf, i
 }
 
 // Batched variant: NB independent transforms of length N stored back to back in `buf`.
-template <int N, int R, int S, int NB, int NT, bool INV>
+template <int N, int R, int S, int NB, int NT, bool INV, bool TT = false, bool PM = false, class MapIn = IdMap, class MapOut = IdMap,
+          int STRIDE = N>
 __device__ __forceinline__ void pass_inplace_batched(float2* buf, int tid, const float2* __restrict__ W) {
     constexpr int NBF = N / R;
     constexpr int ITEMS = NBF * NB;
@@ -319,7 +337,7 @@ __device__ __forceinline__ void pass_inplace_batched(float2* buf, int tid, const
         const int it = tid + i * NT;
         if (it < ITEMS) {
             const int b = it / NBF, t = it - b * NBF;
-            Pass<N, R, S>::load(buf + b * N, t, a[i]);
+            Pass<N, R, S, PM>::template load<MapIn>(buf + b * STRIDE, t, a[i]);
         }
     }
     __syncthreads();
@@ -328,7 +346,7 @@ __device__ __forceinline__ void pass_inplace_batched(float2* buf, int tid, const
         const int it = tid + i * NT;
         if (it < ITEMS) {
             const int b = it / NBF, t = it - b * NBF;
-            Pass<N, R, S>::template compute_store<INV>(buf + b * N, t, a[i], W);
+            Pass<N, R, S, PM>::template compute_store<INV, TT, MapOut>(buf + b * STRIDE, t, a[i], W);
         }
     }
     __syncthreads();
@@ -336,7 +354,7 @@ __device__ __forceinline__ void pass_inplace_batched(float2* buf, int tid, const
 
 // Out-of-place pass src -> dst (both shared memory, distinct): one butterfly at a time per thread (low register
 // pressure), a single barrier at the end.
-template <int N, int R, int S, int NT, bool INV>
+template <int N, int R, int S, int NT, bool INV, bool TT = false, bool PM = false>
 __device__ __forceinline__ void pass_oop(const float2* src, float2* dst, int lt, const float2* __restrict__ W) {
     constexpr int NBF = N / R;
 #pragma unroll
@@ -344,8 +362,8 @@ __device__ __forceinline__ void pass_oop(const float2* src, float2* dst, int lt,
         const int t = t0 + lt;
         if (NBF % NT == 0 || t < NBF) {
             float2 a[R];
-            Pass<N, R, S>::load(src, t, a);
-            Pass<N, R, S>::template compute_store<INV>(dst, t, a, W);
+            Pass<N, R, S, PM>::load(src, t, a);
+            Pass<N, R, S, PM>::template compute_store<INV, TT>(dst, t, a, W);
         }
     }
     __syncthreads();

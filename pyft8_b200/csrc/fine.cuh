@@ -43,8 +43,8 @@ template <> __device__ __forceinline__ float2 load_pair<float>(const float* x, i
 // grid (16, B).  Y: [B][375][256] float2.
 template <typename T>
 __global__ void __launch_bounds__(CS_NT)
-k_cs_cols(const T* __restrict__ audio, float2* __restrict__ Y, const float2* __restrict__ W375,
-          const float2* __restrict__ W96000) {
+k_cs_cols(const T* __restrict__ audio, float2* __restrict__ Y, const float2* __restrict__ TC,
+          const float2* __restrict__ W96000T) {
     extern __shared__ float2 cs_smem[];          // [16][375]
     const int cyc = blockIdx.y, n2_0 = blockIdx.x * CS_COLS;
     const T* x = audio + (size_t)cyc * CYCLE_SAMPLES;
@@ -68,25 +68,29 @@ k_cs_cols(const T* __restrict__ audio, float2* __restrict__ Y, const float2* __r
         }
     }
     __syncthreads();
-    pass_inplace_batched<375, 3, 1, CS_COLS, CS_NT, false>(cs_smem, threadIdx.x, W375);
-    pass_inplace_batched<375, 5, 3, CS_COLS, CS_NT, false>(cs_smem, threadIdx.x, W375);
-    pass_inplace_batched<375, 5, 15, CS_COLS, CS_NT, false>(cs_smem, threadIdx.x, W375);
-    pass_inplace_batched<375, 5, 75, CS_COLS, CS_NT, false>(cs_smem, threadIdx.x, W375);
+    // per-pass twiddle tables [k-1][p]: (3,1) 2 x 125 | (5,3) 4 x 25 | (5,15) 4 x 5; the last pass has none
+    pass_inplace_batched<375, 3, 1, CS_COLS, CS_NT, false, true>(cs_smem, threadIdx.x, TC);
+    pass_inplace_batched<375, 5, 3, CS_COLS, CS_NT, false, true, true>(cs_smem, threadIdx.x, TC + 250);   // p-major: strides 3 / 15
+    pass_inplace_batched<375, 5, 15, CS_COLS, CS_NT, false, true>(cs_smem, threadIdx.x, TC + 350);
+    pass_inplace_batched<375, 5, 75, CS_COLS, CS_NT, false>(cs_smem, threadIdx.x, TC);
     float2* y = Y + (size_t)cyc * CS_N;
     for (int i = threadIdx.x; i < CS_COLS * CS_N1; i += CS_NT) {
         const int k1 = i / CS_COLS, c = i - k1 * CS_COLS;
         const int n2 = n2_0 + c;
-        const float2 w = __ldg(&W96000[n2 * k1]);
+        const float2 w = __ldg(&W96000T[k1 * CS_N2 + n2]);       // = w_96000^(n2 k1), stored [k1][n2] so the load is coalesced
         y[k1 * CS_N2 + n2] = cmul(cs_smem[c * CS_N1 + k1], w);
     }
 }
 
 constexpr int CSR_G = 8;      // k1 values per CTA (plus their mirrors)
+constexpr int CSR_STRIDE = CS_N2 + CS_N2 / 16;
 // grid (24, B): k1 in {0} u [1,187] in groups of 8.  spec: [B][spec_stride] float2, bins <= kmax written.
 __global__ void __launch_bounds__(CS_NT)
 k_cs_rows(const float2* __restrict__ Y, float2* __restrict__ spec, int spec_stride, int kmax,
-          const float2* __restrict__ W256, const float2* __restrict__ W192000) {
-    __shared__ float2 rows[2 * CSR_G][CS_N2];     // [0..7] rows k1, [8..15] mirror rows 375-k1
+          const float2* __restrict__ T256, const float2* __restrict__ W192000) {
+    // [0..7] rows k1, [8..15] mirror rows 375-k1; row stride 272: the intermediate of the two radix-16 passes is stored
+    // with one pad per 16 elements (Pad16Map), otherwise the first pass's stride-16 stores all hit one bank
+    __shared__ float2 rows[2 * CSR_G][CSR_STRIDE];
     const int cyc = blockIdx.y, g0 = blockIdx.x * CSR_G;
     const float2* y = Y + (size_t)cyc * CS_N;
     {
@@ -101,8 +105,8 @@ k_cs_rows(const float2* __restrict__ Y, float2* __restrict__ spec, int spec_stri
         for (int r = 0; r < 2 * CSR_G; ++r) rows[r][threadIdx.x] = v[r];
     }
     __syncthreads();
-    pass_inplace_batched<256, 16, 1, 2 * CSR_G, CS_NT, false>(&rows[0][0], threadIdx.x, W256);
-    pass_inplace_batched<256, 16, 16, 2 * CSR_G, CS_NT, false>(&rows[0][0], threadIdx.x, W256);
+    pass_inplace_batched<256, 16, 1, 2 * CSR_G, CS_NT, false, true, false, IdMap, Pad16Map, CSR_STRIDE>(&rows[0][0], threadIdx.x, T256);    // [15][16]
+    pass_inplace_batched<256, 16, 16, 2 * CSR_G, CS_NT, false, false, false, Pad16Map, IdMap, CSR_STRIDE>(&rows[0][0], threadIdx.x, T256);
     float2* out = spec + (size_t)cyc * spec_stride;
     for (int i = threadIdx.x; i < CSR_G * CS_N2; i += CS_NT) {
         const int k2 = i / CSR_G, r = i - k2 * CSR_G;
@@ -142,7 +146,7 @@ struct FineOut {               // per candidate
 // operands a[p + 640 j] straight from the spectrum: j = 2, 3 are always zero, j = 1 is non-zero only for p < 210 and
 // j = 4 only for p >= 490, so the radix-5 butterfly degenerates to b_k = a0 + a1 w^k + a4 conj(w^k), w = e^{+2 pi i/5}.
 __device__ __forceinline__ void fine_pass1(float2* tmp, const float2* __restrict__ spec, int fb, int tid,
-                                           const float2* __restrict__ W3200, const float* taper) {
+                                           const float2* __restrict__ TF, const float* taper) {
     constexpr int NBF = 640;
 #pragma unroll
     for (int p0 = 0; p0 < NBF; p0 += FINE_NT) {
@@ -173,31 +177,42 @@ __device__ __forceinline__ void fine_pass1(float2* tmp, const float2* __restrict
             }
             tmp[5 * p] = b[0];
 #pragma unroll
-            for (int k = 1; k < 5; ++k) tmp[5 * p + k] = cmulc(b[k], __ldg(&W3200[p * k]));
+            for (int k = 1; k < 5; ++k) tmp[5 * p + k] = cmulc(b[k], __ldg(&TF[(k - 1) * NBF + p]));     // = W3200[p k], stored [k-1][p]
         }
     }
 }
 
 // passes (5,5) (8,25): a -> b -> a, one barrier after each; `a` then holds the operands of the last pass (16,200)
-__device__ __forceinline__ void fine_pass23(float2* a, float2* b, int tid, const float2* __restrict__ W3200) {
-    pass_oop<3200, 5, 5, FINE_NT, true>(a, b, tid, W3200);
-    pass_oop<3200, 8, 25, FINE_NT, true>(b, a, tid, W3200);
+constexpr int FINE_T5_OFF = 4 * 640, FINE_T8_OFF = FINE_T5_OFF + 4 * 128, FINE_TF_LEN = FINE_T8_OFF + 7 * 16;
+__device__ __forceinline__ void fine_pass23(float2* a, float2* b, int tid, const float2* __restrict__ TF) {
+    pass_oop<3200, 5, 5, FINE_NT, true, true, true>(a, b, tid, TF + FINE_T5_OFF);    // p-major: stride-5 loads, stride-25 stores
+    pass_oop<3200, 8, 25, FINE_NT, true, true>(b, a, tid, TF + FINE_T8_OFF);
 }
 
 // Last pass (16,200) restricted to the `len` <= 256 consecutive output samples n0 .. n0+len-1 that the Costas scoring
-// reads (7 symbols x 32 samples, + 14 for the time scan): z[n] = sum_j x[n%200 + 200 j] * e^{+2 pi i j (n/200)/16}.
+// reads (7 symbols x 32 samples, + 14 for the time scan): z[n] = sum_j x[n%200 + 200 j] * w^(j k), k = n/200, w = e^{+2 pi i/16}.
 // A full pass would produce 3200 samples of which the score uses 7 %; only the winning transform gets the full pass.
+// One output per thread, evaluated radix-4 style: j = 4a + b, w^(4 a k) = i^(a k), so with r = k mod 4
+//   y_b = x_b0 + i^r x_b1 + i^2r x_b2 + i^3r x_b3 = (x_b0 +- x_b2) + i^r (x_b1 +- x_b3)      (signs: - for odd r)
+//   z   = y_0 + w^k y_1 + w^2k y_2 + w^3k y_3
+// i.e. 16 loads, multiplications by 0/+-1 only inside y_b (exact), and 3 twiddle multiplies instead of 15.
 __device__ __forceinline__ void fine_pass4_window(const float2* x, float2* zwin, int n0, int len, int tid, const float2* w16) {
     if (tid < len) {
         const int n = n0 + tid;
         const int kk = n / 200, q = n - 200 * kk;
-        float2 acc = x[q];
+        const int r = kk & 3;
+        const float sg = (r & 1) ? -1.0f : 1.0f;                                    // x_b0 + sg x_b2,  x_b1 + sg x_b3
+        const float2 ir = make_float2(r == 0 ? 1.0f : (r == 2 ? -1.0f : 0.0f), r == 1 ? 1.0f : (r == 3 ? -1.0f : 0.0f));   // i^r
+        float2 y[4];
 #pragma unroll
-        for (int j = 1; j < 16; ++j) {
-            const float2 w = w16[(j * kk) & 15];
-            const float2 v = x[q + 200 * j];
-            acc = cmac(acc, v, w);
+        for (int b = 0; b < 4; ++b) {
+            const float2 x0 = x[q + 200 * b], x1 = x[q + 200 * (4 + b)], x2 = x[q + 200 * (8 + b)], x3 = x[q + 200 * (12 + b)];
+            const float2 s = caxpy(sg, x2, x0), t = caxpy(sg, x3, x1);
+            y[b] = cmac(s, t, ir);
         }
+        float2 acc = y[0];
+#pragma unroll
+        for (int b = 1; b < 4; ++b) acc = cmac(acc, y[b], w16[(b * kk) & 15]);
         zwin[tid] = acc;
     }
     __syncthreads();
@@ -260,7 +275,7 @@ constexpr int FINE_SMEM_BYTES = FINE_BUFS * FINE_N * (int)sizeof(float2) + (79 *
 __global__ void __launch_bounds__(FINE_NT, 2)
 k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restrict__ list, const int32_t* __restrict__ count,
        int n_direct, const int32_t* __restrict__ cycle_of, const int16_t* __restrict__ cand_f0,
-       const int16_t* __restrict__ cand_h0, const float2* __restrict__ W3200, FineOut* __restrict__ fo,
+       const int16_t* __restrict__ cand_h0, const float2* __restrict__ TF, FineOut* __restrict__ fo,
        float* __restrict__ llr_fine, float* __restrict__ sig_grid) {
     extern __shared__ float2 fine_smem[];
     float* G = reinterpret_cast<float*>(fine_smem + FINE_BUFS * FINE_N);      // [79][8]
@@ -292,15 +307,15 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         float2 *pb = fine_smem, *pc = fine_smem + FINE_N, *pf = fine_smem + 2 * FINE_N;
         // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT; warp w scores start w.
         //      Middle-Costas windows start at tb0 + tt + 32*(36+k) in [849, 2082] for every reachable h0: never clipped.
-        fine_pass1(pc, sp, fb0, tid, W3200, taper);
+        fine_pass1(pc, sp, fb0, tid, TF, taper);
         __syncthreads();
-        fine_pass23(pc, pf, tid, W3200);
+        fine_pass23(pc, pf, tid, TF);
         fine_pass4_window(pc, zwin, tb0 - 8 + 1152, 238, tid, w16);
         {
             const float sc = costas_rows4(zwin, 2 * warp, 0, lane, tw) + costas_rows4(zwin, 2 * warp, 4, lane, tw);
             if (lane == 0) score[warp] = sc;
         }
-        fine_pass1(pf, sp, fb0 - 32, tid, W3200, taper);             // first frequency tweak, overlapped with the time scan
+        fine_pass1(pf, sp, fb0 - 32, tid, TF, taper);             // first frequency tweak, overlapped with the time scan
         __syncthreads();
         int tt = -8;
         float bestf = score[0];
@@ -313,13 +328,13 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         int best_fi = 4;
         for (int e = 0; e < 8; ++e) {
             const int fi = e < 4 ? e : e + 1;
-            fine_pass23(pc, pf, tid, W3200);                           // pc: last-pass operands of this transform
+            fine_pass23(pc, pf, tid, TF);                           // pc: last-pass operands of this transform
             fine_pass4_window(pc, zwin, tb0 + tt + 1152, 224, tid, w16);
             if (warp < 2) {
                 const float r = costas_rows4(zwin, 0, 4 * warp, lane, tw);
                 if (lane == 0) score[8 + warp] = r;
             }
-            if (e < 7) fine_pass1(pf, sp, fb0 + (-32 + 8 * (e + 1 < 4 ? e + 1 : e + 2)), tid, W3200, taper);
+            if (e < 7) fine_pass1(pf, sp, fb0 + (-32 + 8 * (e + 1 < 4 ? e + 1 : e + 2)), tid, TF, taper);
             __syncthreads();
             const float sc = score[8] + score[9];
             if (sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; float2* t = pb; pb = pc; pc = t; }
@@ -327,7 +342,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         }
         const int ff = -32 + 8 * best_fi;
         // ---- full last pass of the winner, then the final grid (receiver.py:161): four symbol rows per warp
-        pass_oop<3200, 16, 200, FINE_NT, true>(pb, pf, tid, W3200);
+        pass_oop<3200, 16, 200, FINE_NT, true>(pb, pf, tid, TF);
         const float2* z = pf;
         for (int j0 = 4 * warp; j0 < 79; j0 += 4 * (FINE_NT / 32)) {
             const int j = j0 + (lane >> 3);

@@ -40,6 +40,7 @@ struct ft8_handle {
     float* d_hann = nullptr;
     float2 *d_W1920 = nullptr, *d_W3840 = nullptr, *d_W3200 = nullptr, *d_W375 = nullptr, *d_W256 = nullptr,
            *d_W96000 = nullptr, *d_W192000 = nullptr, *d_W32 = nullptr;
+    float2 *d_TS = nullptr, *d_TF = nullptr, *d_TC = nullptr, *d_T256 = nullptr, *d_W96000T = nullptr;   // per-pass twiddle tables [k-1][p]
     float* d_pulse = nullptr;        // GFSK pulse for the synthetic generator
     // batch scratch
     size_t cap_cycles = 0, cap_slots = 0;
@@ -93,6 +94,19 @@ static std::vector<float2> twiddles(int n, int count) {
         w[j] = make_float2((float)cos(a), (float)sin(a));
     }
     return w;
+}
+
+static float2 twiddle1(int n, long long j) {
+    const double a = -2.0 * M_PI * (double)(j % n) / (double)n;
+    return make_float2((float)cos(a), (float)sin(a));
+}
+
+// Per-pass twiddle table of Stockham pass (R, S) of a length-n transform, laid out [k-1][p] (fft.cuh, Pass::compute_store
+// with TT = true): entry = w_n^(p k S), the same value the plain table holds at index p*k*S.
+static void append_pass_table(std::vector<float2>& out, int n, int R, int S) {
+    const int M = n / (R * S);
+    for (int k = 1; k < R; ++k)
+        for (int p = 0; p < M; ++p) out.push_back(twiddle1(n, (long long)p * k * S));
 }
 
 template <typename T> static cudaError_t upload(T** dst, const std::vector<T>& v) {
@@ -254,9 +268,21 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
         CKC(upload(&h->d_W3200, twiddles(3200, 3200)));
         CKC(upload(&h->d_W375, twiddles(375, 375)));
         CKC(upload(&h->d_W256, twiddles(256, 256)));
-        CKC(upload(&h->d_W96000, twiddles(96000, 96000)));
         CKC(upload(&h->d_W192000, twiddles(192000, 96001)));
         CKC(upload(&h->d_W32, twiddles(32, 32)));
+        {   // per-pass tables (coalesced twiddle loads), one buffer per kernel
+            std::vector<float2> ts, tf, tc, t256, w96t;
+            append_pass_table(ts, 1920, 15, 1); append_pass_table(ts, 1920, 8, 15);                              // SP_T8_OFF
+            append_pass_table(tf, 3200, 5, 1); append_pass_table(tf, 3200, 5, 5); append_pass_table(tf, 3200, 8, 25);   // FINE_T*_OFF
+            append_pass_table(tc, 375, 3, 1); append_pass_table(tc, 375, 5, 3); append_pass_table(tc, 375, 5, 15);
+            append_pass_table(t256, 256, 16, 1);
+            w96t.reserve((size_t)CS_N1 * CS_N2);
+            for (int k1 = 0; k1 < CS_N1; ++k1)
+                for (int n2 = 0; n2 < CS_N2; ++n2) w96t.push_back(twiddle1(96000, (long long)n2 * k1));
+            if ((int)ts.size() != SP_T8_OFF + 7 * 16 || (int)tf.size() != FINE_TF_LEN || (int)tc.size() != 370) return fail(nullptr, FT8_E_CUDA, "twiddle table layout");
+            CKC(upload(&h->d_TS, ts)); CKC(upload(&h->d_TF, tf)); CKC(upload(&h->d_TC, tc)); CKC(upload(&h->d_T256, t256));
+            CKC(upload(&h->d_W96000T, w96t));
+        }
         CKC(upload(&h->d_pulse, synth_pulse_table()));
     }
     const size_t B = (size_t)cfg.max_cycles, K = (size_t)cfg.max_cands, N = B * K;
@@ -298,7 +324,7 @@ extern "C" void ft8_destroy(ft8_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* ptrs[] = {h->d_hann, h->d_W1920, h->d_W3840, h->d_W3200, h->d_W375, h->d_W256, h->d_W96000, h->d_W192000, h->d_W32,
+    void* ptrs[] = {h->d_TS, h->d_TF, h->d_TC, h->d_T256, h->d_W96000T, h->d_hann, h->d_W1920, h->d_W3840, h->d_W3200, h->d_W375, h->d_W256, h->d_W96000, h->d_W192000, h->d_W32,
                     h->d_pulse, h->d_audio, h->d_grid, h->d_Y, h->d_spec, h->d_best_score, h->d_best_h0, h->d_f0, h->d_h0, h->d_score,
                     h->d_ncand, h->d_cycle_of, h->d_status, h->d_llr_grid, h->d_grid_sd, h->d_grid_snr, h->d_llr_fine, h->d_fine,
                     h->d_saved, h->d_saved_n, h->d_saved_ap, h->d_bits, h->d_ripass, h->d_rap, h->d_rmethod, h->d_rnits,
@@ -350,10 +376,10 @@ static int launch_spectrogram(ft8_handle* h, const void* d_audio, int dtype, int
     dim3 grid((row_hi - row_lo + SP_ROWS) / SP_ROWS, B);
     const int smem = SP_ROWS * SP_BUFS * 1920 * (int)sizeof(float2);
     if (dtype == FT8_AUDIO_I16)
-        k_spectrogram<int16_t><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const int16_t*)d_audio, d_grid, h->d_hann, h->d_W1920,
+        k_spectrogram<int16_t><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const int16_t*)d_audio, d_grid, h->d_hann, h->d_TS,
                                                                           h->d_W3840, row_lo, row_hi, out_rows, out_row0, fill_row0);
     else
-        k_spectrogram<float><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const float*)d_audio, d_grid, h->d_hann, h->d_W1920,
+        k_spectrogram<float><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const float*)d_audio, d_grid, h->d_hann, h->d_TS,
                                                                         h->d_W3840, row_lo, row_hi, out_rows, out_row0, fill_row0);
     CK(cudaGetLastError());
     return FT8_OK;
@@ -380,11 +406,11 @@ static int launch_cycle_spectrum(ft8_handle* h, const void* d_audio, int dtype, 
         const char* a = (const char*)d_audio + (size_t)b0 * CYCLE_SAMPLES * esz;
         const int smem = CS_COLS * CS_N1 * (int)sizeof(float2);
         if (dtype == FT8_AUDIO_I16)
-            k_cs_cols<int16_t><<<dim3(CS_N2 / CS_COLS, nb), CS_NT, smem, h->stream>>>((const int16_t*)a, h->d_Y, h->d_W375, h->d_W96000);
+            k_cs_cols<int16_t><<<dim3(CS_N2 / CS_COLS, nb), CS_NT, smem, h->stream>>>((const int16_t*)a, h->d_Y, h->d_TC, h->d_W96000T);
         else
-            k_cs_cols<float><<<dim3(CS_N2 / CS_COLS, nb), CS_NT, smem, h->stream>>>((const float*)a, h->d_Y, h->d_W375, h->d_W96000);
+            k_cs_cols<float><<<dim3(CS_N2 / CS_COLS, nb), CS_NT, smem, h->stream>>>((const float*)a, h->d_Y, h->d_TC, h->d_W96000T);
         CK(cudaGetLastError());
-        k_cs_rows<<<dim3(24, nb), CS_NT, 0, h->stream>>>(h->d_Y, d_spec + (size_t)b0 * stride, stride, kmax, h->d_W256, h->d_W192000);
+        k_cs_rows<<<dim3(24, nb), CS_NT, 0, h->stream>>>(h->d_Y, d_spec + (size_t)b0 * stride, stride, kmax, h->d_T256, h->d_W192000);
         CK(cudaGetLastError());
     }
     return FT8_OK;
@@ -559,7 +585,7 @@ extern "C" int ft8_fine(ft8_handle* h, const float* spec, int B, const int32_t* 
     TRY(to_device(h, df0, f0_idx, (size_t)N * 2, mem));
     TRY(to_device(h, dh0, h0_idx, (size_t)N * 2, mem));
     k_fine<<<std::min(persistent_blocks(h, 4), N), FINE_NT, FINE_SMEM_BYTES, h->stream>>>(
-        sp, FT8_SPEC_BINS, nullptr, nullptr, N, dco, df0, dh0, h->d_W3200, dfo, dllr, signal_grid ? dsg : nullptr);
+        sp, FT8_SPEC_BINS, nullptr, nullptr, N, dco, df0, dh0, h->d_TF, dfo, dllr, signal_grid ? dsg : nullptr);
     CK(cudaGetLastError());
     std::vector<FineOut> fo(N);
     CK(cudaMemcpyAsync(fo.data(), dfo, (size_t)N * sizeof(FineOut), cudaMemcpyDeviceToHost, h->stream));
@@ -883,7 +909,7 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
     CK(cudaEventRecord(h->ev[4], h->stream));
     // ipass 1
     k_fine<<<persistent_blocks(h, 4), FINE_NT, FINE_SMEM_BYTES, h->stream>>>(
-        h->d_spec, FINE_SPEC_STRIDE, h->d_list_fine, h->d_counts + 0, 0, h->d_cycle_of, h->d_f0, h->d_h0, h->d_W3200, h->d_fine,
+        h->d_spec, FINE_SPEC_STRIDE, h->d_list_fine, h->d_counts + 0, 0, h->d_cycle_of, h->d_f0, h->d_h0, h->d_TF, h->d_fine,
         h->d_llr_fine, nullptr);
     CK(cudaGetLastError()); ++launches;
     CK(cudaEventRecord(h->ev[5], h->stream));

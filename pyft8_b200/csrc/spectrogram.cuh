@@ -23,6 +23,7 @@ namespace ft8 {
 constexpr int SP_ROWS = SP_ROWS_N;  // rows per CTA
 constexpr int SP_BUFS = 1;          // one in-place buffer per row (ping-pong buffers measured slower)
 constexpr int SP_NT = 128;          // threads per row
+constexpr int SP_T8_OFF = 14 * 128;  // per-pass twiddle tables of the 1920-point transform: [(15,1): 14 x 128 | (8,15): 7 x 16]
 constexpr int GRID_ROWS = 376, GRID_COLS = 976, CYCLE_SAMPLES = 180000, NFFT_S = 3840, HOP = 480;
 
 // two consecutive samples starting at an even index (one 32-bit / 64-bit load)
@@ -38,7 +39,7 @@ __device__ __forceinline__ float2 load_sample_pair(const float* a, int i) { retu
 template <typename T>
 __global__ void __launch_bounds__(SP_ROWS* SP_NT, SP_MIN_BLOCKS)
 k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float* __restrict__ hann,
-              const float2* __restrict__ W1920, const float2* __restrict__ W3840, int row_lo, int row_hi, int out_rows,
+              const float2* __restrict__ TS, const float2* __restrict__ W3840, int row_lo, int row_hi, int out_rows,
               int out_row0, int fill_row0) {
     extern __shared__ float2 sp_smem[];
     const int cyc = blockIdx.y;
@@ -69,11 +70,11 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
             }
             a[j] = z;
         }
-        Pass<1920, 15, 1>::template compute_store<false>(buf, lt, a, W1920);
+        Pass<1920, 15, 1>::template compute_store<false, true>(buf, lt, a, TS);
         __syncthreads();
     }
-    pass_inplace<1920, 8, 15, SP_NT, false>(buf, lt, W1920, CtaSync());
-    pass_oop<1920, 16, 120, SP_NT, false>(buf, buf, lt, W1920);   // last pass (M = 1): each thread rewrites the 16 positions it read
+    pass_inplace<1920, 8, 15, SP_NT, false, CtaSync, true>(buf, lt, TS + SP_T8_OFF, CtaSync());
+    pass_oop<1920, 16, 120, SP_NT, false>(buf, buf, lt, TS);   // last pass (M = 1): each thread rewrites the 16 positions it read
 
     // untangle the real transform for bins 0..975 and write dB
     if (live) {
