@@ -189,6 +189,56 @@ __device__ __forceinline__ void fine_pass23(float2* a, float2* b, int tid, const
     pass_oop<3200, 8, 25, FINE_NT, true, true>(b, a, tid, TF + FINE_T8_OFF);
 }
 
+// Passes (5,1) and (5,5) fused, one thread per p2 < 128 (four warps): the thread builds the five sparse first-pass
+// butterflies p = p2 + 128 j in registers (25 values, same arithmetic as fine_pass1), then runs the five second-pass
+// butterflies (p2, q) on them and stores the second-pass output y[q + 25 p2 + 5 k] (stride 25 across lanes: no bank
+// conflict).  Against the two separate passes this drops the 3200-element store + reload of the intermediate and 16 of the
+// 20 second-pass twiddle loads per p2 -- about 30 % of the kernel's traffic on the shared-memory / L1 pipe, which is what
+// bounds it -- and needs no shared-memory input, so the other four warps can score the previous transform meanwhile.
+__device__ __forceinline__ void fine_pass12(float2* dst, const float2* __restrict__ spec, int fb, int p2,
+                                            const float2* __restrict__ TF, const float* taper) {
+    float2 x[5][5];                                                 // x[j][k]: output k of first-pass butterfly p2 + 128 j
+    const float2 w1 = make_float2(0.30901699437494742410f, 0.95105651629515357212f);
+    const float2 w2 = make_float2(-0.80901699437494742410f, 0.58778525229247312917f);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int p = p2 + 128 * j;
+        const float2 a0 = __ldg(&spec[fb + p]);
+        float2 b[5] = {a0, a0, a0, a0, a0};
+        if (j < 2 && p < 210) {                                     // i = p + 640 in [640, 850)
+            float2 a1 = __ldg(&spec[fb + p + 640]);
+            if (p >= 110) a1 = cscale(taper[p - 110], a1);
+            b[0] = cadd(a0, a1);
+            b[1] = cadd(a0, cmul(a1, w1));
+            b[2] = cadd(a0, cmul(a1, w2));
+            b[3] = cadd(a0, cmulc(a1, w2));
+            b[4] = cadd(a0, cmulc(a1, w1));
+        } else if (j > 2 && p >= 490) {                             // i = p + 2560 in [3050, 3200)
+            float2 a4 = __ldg(&spec[fb + p - 640]);
+            if (p < 590) a4 = cscale(taper[p - 490], a4);
+            b[0] = cadd(a0, a4);
+            b[1] = cadd(a0, cmulc(a4, w1));
+            b[2] = cadd(a0, cmulc(a4, w2));
+            b[3] = cadd(a0, cmul(a4, w2));
+            b[4] = cadd(a0, cmul(a4, w1));
+        }
+        x[j][0] = b[0];
+#pragma unroll
+        for (int k = 1; k < 5; ++k) x[j][k] = cmulc(b[k], __ldg(&TF[(k - 1) * 640 + p]));
+    }
+    float2 w[4];
+#pragma unroll
+    for (int k = 1; k < 5; ++k) w[k - 1] = __ldg(&TF[FINE_T5_OFF + (k - 1) * 128 + p2]);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        float2 a[5] = {x[0][q], x[1][q], x[2][q], x[3][q], x[4][q]};
+        Dft<5, true>::run(a);
+        dst[q + 25 * p2] = a[0];
+#pragma unroll
+        for (int k = 1; k < 5; ++k) dst[q + 25 * p2 + 5 * k] = cmulc(a[k], w[k - 1]);
+    }
+}
+
 // Last pass (16,200) restricted to the `len` <= 256 consecutive output samples n0 .. n0+len-1 that the Costas scoring
 // reads (7 symbols x 32 samples, + 14 for the time scan): z[n] = sum_j x[n%200 + 200 j] * w^(j k), k = n/200, w = e^{+2 pi i/16}.
 // A full pass would produce 3200 samples of which the score uses 7 %; only the winning transform gets the full pass.
@@ -196,9 +246,11 @@ __device__ __forceinline__ void fine_pass23(float2* a, float2* b, int tid, const
 //   y_b = x_b0 + i^r x_b1 + i^2r x_b2 + i^3r x_b3 = (x_b0 +- x_b2) + i^r (x_b1 +- x_b3)      (signs: - for odd r)
 //   z   = y_0 + w^k y_1 + w^2k y_2 + w^3k y_3
 // i.e. 16 loads, multiplications by 0/+-1 only inside y_b (exact), and 3 twiddle multiplies instead of 15.
+// Executed by the 128 threads of warps 0-3 (two outputs each); no barrier inside.
 __device__ __forceinline__ void fine_pass4_window(const float2* x, float2* zwin, int n0, int len, int tid, const float2* w16) {
-    if (tid < len) {
-        const int n = n0 + tid;
+#pragma unroll
+    for (int o = tid; o < 256; o += 128) if (o < len) {
+        const int n = n0 + o;
         const int kk = n / 200, q = n - 200 * kk;
         const int r = kk & 3;
         const float sg = (r & 1) ? -1.0f : 1.0f;                                    // x_b0 + sg x_b2,  x_b1 + sg x_b3
@@ -213,9 +265,8 @@ __device__ __forceinline__ void fine_pass4_window(const float2* x, float2* zwin,
         float2 acc = y[0];
 #pragma unroll
         for (int b = 1; b < 4; ++b) acc = cmac(acc, y[b], w16[(b * kk) & 15]);
-        zwin[tid] = acc;
+        zwin[o] = acc;
     }
-    __syncthreads();
 }
 
 // 32-sample symbol DFTs (receiver.py:195), FOUR windows per warp: lane = 8*g + m serves window g (0..3) and holds its
@@ -262,7 +313,7 @@ __device__ __forceinline__ float costas_rows4(const float2* z, int z0, int k0, i
     const int k = k0 + (lane >> 3), bin = lane & 7;
     const float g = dft32x4_mag(z, z0 + 32 * min(k, 6), lane, tw);
     float c = 0.0f;
-    if (k < 7 && bin < 7) c = (bin == c_costas[k]) ? g : g * (-1.0f / 6.0f);
+    if (k < 7 && bin < 7) c = (bin == ((0x2560413 >> (4 * k)) & 7)) ? g : g * (-1.0f / 6.0f);   // Costas 3,1,4,0,6,5,2 as nibbles (a lane-indexed __constant__ read would serialise)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     return c;
@@ -300,50 +351,60 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         const float2* sp = spec + (size_t)cyc * spec_stride;
         const int fb0 = 50 * f0;                                   // int(0.5 + 16*fHz), fHz = 3.125*f0
         const int tb0 = (h0 >= 0) ? 8 * h0 : 8 * h0 + 1;           // int(0.5 + 200*tsec) truncates toward zero
-        // Three 3200-sample buffers rotate: pb = last-pass operands of the best transform so far, pc/pf = work.
-        // Per transform: first pass (global -> pc), passes (5,5),(8,25) (pc -> pf -> pc), then only the samples the
-        // Costas score reads are produced by the windowed last pass.  The cheap first pass of the NEXT transform shares
-        // a barrier phase with the scoring of the current one (2 of 8 warps).
-        float2 *pb = fine_smem, *pc = fine_smem + FINE_N, *pf = fine_smem + 2 * FINE_N;
-        // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT; warp w scores start w.
+        // Three 3200-sample buffers: px = second-pass output of the transform being built, po = last-pass operands of the
+        // transform being scored, pb = last-pass operands of the best transform so far.  Per transform there are two
+        // barrier phases: (A) all warps run pass (8,25) px -> po; (B) warps 0-3 produce the samples the Costas score reads
+        // (windowed last pass) and score them, while warps 4-7 build the NEXT transform's fused passes (5,1)(5,5) from
+        // global memory into px.
+        float2 *px = fine_smem, *po = fine_smem + FINE_N, *pb = fine_smem + 2 * FINE_N;
+        // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT.
         //      Middle-Costas windows start at tb0 + tt + 32*(36+k) in [849, 2082] for every reachable h0: never clipped.
-        fine_pass1(pc, sp, fb0, tid, TF, taper);
+        if (warp >= 4) fine_pass12(px, sp, fb0, tid - 128, TF, taper);
         __syncthreads();
-        fine_pass23(pc, pf, tid, TF);
-        fine_pass4_window(pc, zwin, tb0 - 8 + 1152, 238, tid, w16);
-        {
-            const float sc = costas_rows4(zwin, 2 * warp, 0, lane, tw) + costas_rows4(zwin, 2 * warp, 4, lane, tw);
-            if (lane == 0) score[warp] = sc;
+        pass_oop<3200, 8, 25, FINE_NT, true, true>(px, po, tid, TF + FINE_T8_OFF);
+        if (warp < 4) {
+            fine_pass4_window(po, zwin, tb0 - 8 + 1152, 238, tid, w16);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // warp w scores window starts 2w and 2w+1 (tt = -8 + 2*start)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int st = 2 * warp + u;
+                const float sc = costas_rows4(zwin, 2 * st, 0, lane, tw) + costas_rows4(zwin, 2 * st, 4, lane, tw);
+                if (lane == 0) score[st] = sc;
+            }
+        } else {
+            fine_pass12(px, sp, fb0 - 32, tid - 128, TF, taper);     // first frequency tweak, built during the time scan
         }
-        fine_pass1(pf, sp, fb0 - 32, tid, TF, taper);             // first frequency tweak, overlapped with the time scan
         __syncthreads();
         int tt = -8;
         float bestf = score[0];
         for (int ti = 1; ti < 8; ++ti) if (score[ti] > bestf) { bestf = score[ti]; tt = -8 + 2 * ti; }   // first maximum
         // ---- frequency scan at the chosen time tweak (receiver.py:154-159).  The ftweak = 0 evaluation is the time-scan
-        // score at tt (same baseband, same window starts); the other 8 are built in the two buffers that do not hold the
-        // best so far.  "First maximum in ascending ftweak order" = larger score, or equal score and smaller index.
-        // Warps 0 and 1 score Costas symbols 0..3 and 4..6.
-        { float2* t = pb; pb = pc; pc = pf; pf = t; }                 // best = ftweak 0; pc = first-pass output; pf = free
+        // score at tt (same baseband, same window starts).  "First maximum in ascending ftweak order" = larger score, or
+        // equal score and smaller index.  Warps 0 and 1 score Costas symbols 0..3 and 4..6.
+        { float2* t = pb; pb = po; po = t; }                          // best = ftweak 0
         int best_fi = 4;
         for (int e = 0; e < 8; ++e) {
             const int fi = e < 4 ? e : e + 1;
-            fine_pass23(pc, pf, tid, TF);                           // pc: last-pass operands of this transform
-            fine_pass4_window(pc, zwin, tb0 + tt + 1152, 224, tid, w16);
-            if (warp < 2) {
-                const float r = costas_rows4(zwin, 0, 4 * warp, lane, tw);
-                if (lane == 0) score[8 + warp] = r;
+            pass_oop<3200, 8, 25, FINE_NT, true, true>(px, po, tid, TF + FINE_T8_OFF);
+            if (warp < 4) {
+                fine_pass4_window(po, zwin, tb0 + tt + 1152, 224, tid, w16);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp < 2) {
+                    const float r = costas_rows4(zwin, 0, 4 * warp, lane, tw);
+                    if (lane == 0) score[8 + warp] = r;
+                }
+            } else if (e < 7) {
+                fine_pass12(px, sp, fb0 + (-32 + 8 * (e + 1 < 4 ? e + 1 : e + 2)), tid - 128, TF, taper);
             }
-            if (e < 7) fine_pass1(pf, sp, fb0 + (-32 + 8 * (e + 1 < 4 ? e + 1 : e + 2)), tid, TF, taper);
             __syncthreads();
             const float sc = score[8] + score[9];
-            if (sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; float2* t = pb; pb = pc; pc = t; }
-            { float2* t = pc; pc = pf; pf = t; }                       // pc = next first-pass output, pf = free
+            if (sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; float2* t = pb; pb = po; po = t; }
         }
         const int ff = -32 + 8 * best_fi;
         // ---- full last pass of the winner, then the final grid (receiver.py:161): four symbol rows per warp
-        pass_oop<3200, 16, 200, FINE_NT, true>(pb, pf, tid, TF);
-        const float2* z = pf;
+        pass_oop<3200, 16, 200, FINE_NT, true>(pb, po, tid, TF);
+        const float2* z = po;
         for (int j0 = 4 * warp; j0 < 79; j0 += 4 * (FINE_NT / 32)) {
             const int j = j0 + (lane >> 3);
             const float g = dft32x4_mag(z, clip_start(tb0 + tt + 32 * min(j, 78)), lane, tw);
