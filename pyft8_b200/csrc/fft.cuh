@@ -18,14 +18,17 @@ namespace ft8 {
 
 // ---- complex helpers.  Two implementations with the SAME rounding sequence (products rounded once, fma exactly where
 // the formulas quoted below have fmaf), so they produce bit-identical results:
-//   * scalar FFMA/FADD/FMUL (default);
-//   * -DFT8_PACKED_F32X2: Blackwell packed fp32x2 (FFMA2 / FADD2 / FMUL2, one instruction per complex number; ptxas
-//     folds operand swaps, scalar broadcasts and per-half sign changes into modifiers such as R.F32x2.LO_HI.NP / R.F32,
-//     so a complex multiply is 2 instructions and a multiply by +-i inside an add is free).
+//   * default: Blackwell packed fp32x2 (FFMA2 / FADD2 / FMUL2, one instruction per complex number; ptxas folds operand
+//     swaps, scalar broadcasts and per-half sign changes into modifiers such as R.F32x2.LO_HI.NP / R.F32, so a complex
+//     multiply is 2 instructions and a multiply by +-i inside an add is free);
+//   * -DFT8_SCALAR_F32: plain FFMA / FADD / FMUL.
 // Measured on B200 (tools/micro/ffma2_bench.cu, tools/variant_bench.py): FFMA2 sustains the FFMA flop rate with half the
-// issue slots (72 Tflop/s either way); the packed build has 21 % fewer instructions in k_spectrogram (9.08 -> 8.65 ms)
-// but k_fine, which waits on barriers and the shared-memory pipe rather than on issue slots, gets 1.2 % slower
-// (71.5 -> 72.4 ms), so the whole step does not gain and the default stays scalar.
+// issue slots (72 Tflop/s either way).  While the FFT kernels were bound by the shared-memory / L1 pipe the packed build
+// gained nothing (k_fine even lost 1 %); after the twiddle-table and pass-fusion work it is 2 % faster on the whole step
+// (k_spectrogram 8.15 -> 7.91 ms, k_fine 54.0 -> 52.0 ms), records bit-identical.
+#ifndef FT8_SCALAR_F32
+#define FT8_PACKED_F32X2 1
+#endif
 #ifdef FT8_PACKED_F32X2
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
