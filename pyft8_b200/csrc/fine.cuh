@@ -344,6 +344,13 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
 #pragma unroll
     for (int t = 0; t < 8; ++t) tw[t] = w32[(t * (lane & 7)) & 31];
     const int n_items = list ? *count : n_direct;
+    // the first transform of the CTA's first item; every later item's first transform is built by the producer warps
+    // during the final stage of the item before it
+    if (warp >= 4 && (int)blockIdx.x < n_items) {
+        const int slot = list ? list[blockIdx.x] : (int)blockIdx.x;
+        fine_pass12(fine_smem, spec + (size_t)cycle_of[slot] * spec_stride, 50 * cand_f0[slot], tid - 128, TF, taper);
+    }
+    __syncthreads();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int slot = list ? list[item] : item;
         const int cyc = cycle_of[slot];
@@ -359,8 +366,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         float2 *px = fine_smem, *po = fine_smem + FINE_N, *pb = fine_smem + 2 * FINE_N;
         // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT.
         //      Middle-Costas windows start at tb0 + tt + 32*(36+k) in [849, 2082] for every reachable h0: never clipped.
-        if (warp >= 4) fine_pass12(px, sp, fb0, tid - 128, TF, taper);
-        __syncthreads();
+        //      px already holds the fused first passes of this item's ftweak = 0 transform.
         pass_oop<3200, 8, 25, FINE_NT, true, true>(px, po, tid, TF + FINE_T8_OFF);
         if (warp < 4) {
             fine_pass4_window(po, zwin, tb0 - 8 + 1152, 238, tid, w16);
@@ -402,41 +408,51 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
             if (sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; float2* t = pb; pb = po; po = t; }
         }
         const int ff = -32 + 8 * best_fi;
-        // ---- full last pass of the winner, then the final grid (receiver.py:161): four symbol rows per warp
+        // ---- full last pass of the winner, then the final grid (receiver.py:161) by the consumer warps (four symbol rows
+        //      per warp and call) and the Costas count + LLRs by warp 0, while the producer warps already build the first
+        //      transform of this CTA's next item into px (unused during this stage)
         pass_oop<3200, 16, 200, FINE_NT, true>(pb, po, tid, TF);
-        const float2* z = po;
-        for (int j0 = 4 * warp; j0 < 79; j0 += 4 * (FINE_NT / 32)) {
-            const int j = j0 + (lane >> 3);
-            const float g = dft32x4_mag(z, clip_start(tb0 + tt + 32 * min(j, 78)), lane, tw);
-            if (j < 79) G[j * 8 + (lane & 7)] = g;
-        }
-        __syncthreads();
-        if (sig_grid) for (int i = tid; i < 79 * 8; i += FINE_NT) sig_grid[(size_t)slot * 632 + i] = G[i];
-        if (tid < 32) {
-            int hit = 0;
-            if (lane < 21) {
-                const int blk = lane / 7, k = lane - 7 * blk;
-                const int row = (blk == 0) ? k : (blk == 1 ? 36 + k : 72 + k);
-                int am = 0;
-                float mv = G[row * 8];
-                for (int t = 1; t < 8; ++t) if (G[row * 8 + t] > mv) { mv = G[row * 8 + t]; am = t; }
-                hit = (am == c_costas[k]) ? 1 : 0;
+        if (warp < 4) {
+            const float2* z = po;
+            for (int j0 = 4 * warp; j0 < 79; j0 += 16) {
+                const int j = j0 + (lane >> 3);
+                const float g = dft32x4_mag(z, clip_start(tb0 + tt + 32 * min(j, 78)), lane, tw);
+                if (j < 79) G[j * 8 + (lane & 7)] = g;
             }
-            const int nsync = __reduce_add_sync(0xffffffffu, hit);
-            float p[2][8];
-            if (lane < 29) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (sig_grid) for (int i = tid; i < 79 * 8; i += 128) sig_grid[(size_t)slot * 632 + i] = G[i];
+            if (tid < 32) {
+                int hit = 0;
+                if (lane < 21) {
+                    const int blk = lane / 7, k = lane - 7 * blk;
+                    const int row = (blk == 0) ? k : (blk == 1 ? 36 + k : 72 + k);
+                    int am = 0;
+                    float mv = G[row * 8];
+                    for (int t = 1; t < 8; ++t) if (G[row * 8 + t] > mv) { mv = G[row * 8 + t]; am = t; }
+                    hit = (am == ((0x2560413 >> (4 * k)) & 7)) ? 1 : 0;
+                }
+                const int nsync = __reduce_add_sync(0xffffffffu, hit);
+                float p[2][8];
+                if (lane < 29) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int sym = c_payload_sym[lane + 29 * q];
+                    for (int q = 0; q < 2; ++q) {
+                        const int sym = c_payload_sym[lane + 29 * q];
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) p[q][t] = 20.0f * log10f(G[sym * 8 + t]);
+                        for (int t = 0; t < 8; ++t) p[q][t] = 20.0f * log10f(G[sym * 8 + t]);
+                    }
+                }
+                float sd; int snr;
+                llr_from_payload_warp(p, lane, llr_fine + (size_t)slot * 174, sd, snr);
+                if (lane == 0) {
+                    FineOut o; o.tt = tt; o.ff = ff; o.nsync = nsync; o.sd = sd; o.snr = snr;
+                    fo[slot] = o;
                 }
             }
-            float sd; int snr;
-            llr_from_payload_warp(p, lane, llr_fine + (size_t)slot * 174, sd, snr);
-            if (lane == 0) {
-                FineOut o; o.tt = tt; o.ff = ff; o.nsync = nsync; o.sd = sd; o.snr = snr;
-                fo[slot] = o;
+        } else {
+            const int nitem = item + gridDim.x;
+            if (nitem < n_items) {
+                const int nslot = list ? list[nitem] : nitem;
+                fine_pass12(px, spec + (size_t)cycle_of[nslot] * spec_stride, 50 * cand_f0[nslot], tid - 128, TF, taper);
             }
         }
         __syncthreads();
