@@ -30,6 +30,10 @@ constexpr int CS_N = 96000, CS_N1 = 375, CS_N2 = 256, CS_COLS = 16, CS_NT = 256;
 constexpr int FINE_SPEC_STRIDE = 49152;
 constexpr int FINE_N = 3200, FINE_NT = 256;
 #define FINE_BUFS 3        // best-so-far + baseband being built + FFT scratch (2-buffer variants measured 11 % slower)
+// Last-pass operand buffers (po, pb) are stored with one pad element per 200 (index q + 201 j instead of q + 200 j): the
+// stores of pass (8,25) then walk the banks continuously across the run boundaries of a warp (ncu: 22 % of this kernel's
+// shared-store wavefronts were bank-conflict replays without it), the loads of the last pass stay consecutive in q.
+constexpr int FINE_NP = FINE_N + FINE_N / 200;
 
 template <typename T> __device__ __forceinline__ float2 load_pair(const T* x, int n);
 template <> __device__ __forceinline__ float2 load_pair<int16_t>(const int16_t* x, int n) {
@@ -239,6 +243,40 @@ __device__ __forceinline__ void fine_pass12(float2* dst, const float2* __restric
     }
 }
 
+// Pass (8,25) px -> po by all 256 threads; output in the padded operand layout: element q + 25 (8 p + k) goes to
+// q + 201 p + 25 k (q + 25 k < 200).  One barrier at the end.
+__device__ __forceinline__ void fine_pass3(const float2* src, float2* dst, int tid, const float2* __restrict__ TF) {
+#pragma unroll
+    for (int t0 = 0; t0 < 400; t0 += FINE_NT) {
+        const int t = t0 + tid;
+        if (t < 400) {
+            const int p = t / 25, q = t - 25 * p;
+            float2 a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = src[t + 400 * j];
+            Dft<8, true>::run(a);
+            float2* d = dst + q + 201 * p;
+            d[0] = a[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) d[25 * k] = cmulc(a[k], __ldg(&TF[FINE_T8_OFF + (k - 1) * 16 + p]));
+        }
+    }
+    __syncthreads();
+}
+
+// Full last pass (16,200) of the winner: padded operands pb -> natural-order samples in dst.  One barrier at the end.
+__device__ __forceinline__ void fine_last_full(const float2* src, float2* dst, int tid) {
+    if (tid < 200) {
+        float2 a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = src[tid + 201 * j];
+        Dft<16, true>::run(a);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dst[tid + 200 * k] = a[k];
+    }
+    __syncthreads();
+}
+
 // Last pass (16,200) restricted to the `len` <= 256 consecutive output samples n0 .. n0+len-1 that the Costas scoring
 // reads (7 symbols x 32 samples, + 14 for the time scan): z[n] = sum_j x[n%200 + 200 j] * w^(j k), k = n/200, w = e^{+2 pi i/16}.
 // A full pass would produce 3200 samples of which the score uses 7 %; only the winning transform gets the full pass.
@@ -258,7 +296,7 @@ __device__ __forceinline__ void fine_pass4_window(const float2* x, float2* zwin,
         float2 y[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const float2 x0 = x[q + 200 * b], x1 = x[q + 200 * (4 + b)], x2 = x[q + 200 * (8 + b)], x3 = x[q + 200 * (12 + b)];
+            const float2 x0 = x[q + 201 * b], x1 = x[q + 201 * (4 + b)], x2 = x[q + 201 * (8 + b)], x3 = x[q + 201 * (12 + b)];   // padded operand layout
             const float2 s = caxpy(sg, x2, x0), t = caxpy(sg, x3, x1);
             y[b] = cmac(s, t, ir);
         }
@@ -319,7 +357,7 @@ __device__ __forceinline__ float costas_rows4(const float2* z, int z0, int k0, i
     return c;
 }
 
-constexpr int FINE_SMEM_BYTES = FINE_BUFS * FINE_N * (int)sizeof(float2) + (79 * 8 + 16 + 100) * (int)sizeof(float) + (32 + 16 + 256) * (int)sizeof(float2);
+constexpr int FINE_SMEM_BYTES = (FINE_N + 2 * FINE_NP) * (int)sizeof(float2) + (79 * 8 + 16 + 100) * (int)sizeof(float) + (32 + 16 + 256) * (int)sizeof(float2);
 
 // One CTA per work item (grid-stride over list[0..*count)).  cand arrays are indexed by the global slot id.
 // spec: [B][spec_stride] float2.  Outputs per slot: fo[slot], llr_fine[slot][174], optional sig_grid[slot][79][8].
@@ -329,7 +367,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
        const int16_t* __restrict__ cand_h0, const float2* __restrict__ TF, FineOut* __restrict__ fo,
        float* __restrict__ llr_fine, float* __restrict__ sig_grid) {
     extern __shared__ float2 fine_smem[];
-    float* G = reinterpret_cast<float*>(fine_smem + FINE_BUFS * FINE_N);      // [79][8]
+    float* G = reinterpret_cast<float*>(fine_smem + FINE_N + 2 * FINE_NP);      // [79][8]
     float* score = G + 79 * 8;                                        // [16]
     float* taper = score + 16;                                        // [100]
     float2* w32 = reinterpret_cast<float2*>(taper + 100);             // [32]  exp(-2 pi i m/32)
@@ -363,11 +401,11 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         // barrier phases: (A) all warps run pass (8,25) px -> po; (B) warps 0-3 produce the samples the Costas score reads
         // (windowed last pass) and score them, while warps 4-7 build the NEXT transform's fused passes (5,1)(5,5) from
         // global memory into px.
-        float2 *px = fine_smem, *po = fine_smem + FINE_N, *pb = fine_smem + 2 * FINE_N;
+        float2 *px = fine_smem, *po = fine_smem + FINE_N, *pb = fine_smem + FINE_N + FINE_NP;
         // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT.
         //      Middle-Costas windows start at tb0 + tt + 32*(36+k) in [849, 2082] for every reachable h0: never clipped.
         //      px already holds the fused first passes of this item's ftweak = 0 transform.
-        pass_oop<3200, 8, 25, FINE_NT, true, true>(px, po, tid, TF + FINE_T8_OFF);
+        fine_pass3(px, po, tid, TF);
         if (warp < 4) {
             fine_pass4_window(po, zwin, tb0 - 8 + 1152, 238, tid, w16);
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -392,7 +430,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         int best_fi = 4;
         for (int e = 0; e < 8; ++e) {
             const int fi = e < 4 ? e : e + 1;
-            pass_oop<3200, 8, 25, FINE_NT, true, true>(px, po, tid, TF + FINE_T8_OFF);
+            fine_pass3(px, po, tid, TF);
             if (warp < 4) {
                 fine_pass4_window(po, zwin, tb0 + tt + 1152, 224, tid, w16);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -411,7 +449,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         // ---- full last pass of the winner, then the final grid (receiver.py:161) by the consumer warps (four symbol rows
         //      per warp and call) and the Costas count + LLRs by warp 0, while the producer warps already build the first
         //      transform of this CTA's next item into px (unused during this stage)
-        pass_oop<3200, 16, 200, FINE_NT, true>(pb, po, tid, TF);
+        fine_last_full(pb, po, tid);
         if (warp < 4) {
             const float2* z = po;
             for (int j0 = 4 * warp; j0 < 79; j0 += 16) {

@@ -130,6 +130,7 @@ k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows
             }
         }
         float sd; int snr;
+        __syncwarp();                             // the previous slot's readers of llr0 are done (racecheck: write-after-read)
         llr_from_payload_warp(p, lane, llr0, sd, snr);
         __syncwarp();
         for (int i = lane; i < 174; i += 32) cs.llr_grid[(size_t)slot * 174 + i] = llr0[i];
