@@ -311,8 +311,8 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
         CKC(cudaMemcpy(h->d_cycle_of, co.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     CKC(cudaFuncSetAttribute(k_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, FINE_SMEM_BYTES));
-    CKC(cudaFuncSetAttribute(k_spectrogram<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_ROWS * SP_BUFS * 1920 * (int)sizeof(float2)));
-    CKC(cudaFuncSetAttribute(k_spectrogram<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_ROWS * SP_BUFS * 1920 * (int)sizeof(float2)));
+    CKC(cudaFuncSetAttribute(k_spectrogram<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2)));
+    CKC(cudaFuncSetAttribute(k_spectrogram<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2)));
     CKC(cudaFuncSetAttribute(k_sync_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
     CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -374,7 +374,7 @@ static CandState cand_state(ft8_handle* h) {
 static int launch_spectrogram(ft8_handle* h, const void* d_audio, int dtype, int B, float* d_grid, int row_lo = 1,
                               int row_hi = 375, int out_rows = GRID_ROWS, int out_row0 = 0, int fill_row0 = 1) {
     dim3 grid((row_hi - row_lo + SP_ROWS) / SP_ROWS, B);
-    const int smem = SP_ROWS * SP_BUFS * 1920 * (int)sizeof(float2);
+    const int smem = SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2);
     if (dtype == FT8_AUDIO_I16)
         k_spectrogram<int16_t><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const int16_t*)d_audio, d_grid, h->d_hann, h->d_TS,
                                                                           h->d_W3840, row_lo, row_hi, out_rows, out_row0, fill_row0);

@@ -23,6 +23,7 @@ namespace ft8 {
 constexpr int SP_ROWS = SP_ROWS_N;  // rows per CTA
 constexpr int SP_BUFS = 1;          // one in-place buffer per row (ping-pong buffers measured slower)
 constexpr int SP_NT = 128;          // threads per row
+constexpr int SP_BUF_LEN = 1936;      // 1920 + one pad element per 120 (the layout after the second pass)
 constexpr int SP_T8_OFF = 14 * 128;  // per-pass twiddle tables of the 1920-point transform: [(15,1): 14 x 128 | (8,15): 7 x 16]
 constexpr int GRID_ROWS = 376, GRID_COLS = 976, CYCLE_SAMPLES = 180000, NFFT_S = 3840, HOP = 480;
 
@@ -46,7 +47,7 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
     const int g = threadIdx.x / SP_NT, lt = threadIdx.x % SP_NT;
     const int h = row_lo + blockIdx.x * SP_ROWS + g;      // grid row = window ending at sample 480*h
     const bool live = h <= row_hi;
-    float2* buf = sp_smem + g * 1920 * SP_BUFS;
+    float2* buf = sp_smem + g * SP_BUF_LEN * SP_BUFS;
     const T* x = audio + (size_t)cyc * CYCLE_SAMPLES;
     float* out = grid + (size_t)cyc * out_rows * GRID_COLS;
     if (blockIdx.x == 0 && fill_row0) {
@@ -73,15 +74,56 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
         Pass<1920, 15, 1>::template compute_store<false, true>(buf, lt, a, TS);
         __syncthreads();
     }
-    pass_inplace<1920, 8, 15, SP_NT, false, CtaSync, true>(buf, lt, TS + SP_T8_OFF, CtaSync());
-    pass_oop<1920, 16, 120, SP_NT, false>(buf, buf, lt, TS);   // last pass (M = 1): each thread rewrites the 16 positions it read
+    // pass (R=8, S=15, M=16), p-major: butterflies t = lt and lt + 128 share p = lt % 16, so the 7 twiddles are loaded once
+    // (16 consecutive entries per warp request); loads have stride 15 elements (odd: no bank conflict); the output goes to
+    // the padded layout i + i/120 (element q + 120 p + 15 k -> q + 121 p + 15 k, stride 121 across lanes: no conflict --
+    // unpadded, 25 % of this kernel's shared-store wavefronts were conflict replays).
+    {
+        const int p = lt & 15, q0 = lt >> 4;                       // q = q0 and q0 + 8 (second butterfly exists for q0 < 7)
+        float2 w[7];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) w[k - 1] = __ldg(&TS[SP_T8_OFF + (k - 1) * 16 + p]);
+        float2 a[2][8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int q = q0 + 8 * i;
+            if (q < 15) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[i][j] = buf[q + 15 * (p + 16 * j)];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int q = q0 + 8 * i;
+            if (q < 15) {
+                Dft<8, false>::run(a[i]);
+                float2* d = buf + q + 121 * p;
+                d[0] = a[i][0];
+#pragma unroll
+                for (int k = 1; k < 8; ++k) d[15 * k] = cmul(a[i][k], w[k - 1]);
+            }
+        }
+        __syncthreads();
+    }
+    // last pass (R=16, S=120, M=1) on the padded layout, in place: each thread rewrites the 16 positions it read
+    if (lt < 120) {
+        float2 a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = buf[lt + 121 * j];
+        Dft<16, false>::run(a);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) buf[lt + 121 * k] = a[k];
+    }
+    __syncthreads();
 
     // untangle the real transform for bins 0..975 and write dB
     if (live) {
         float* row = out + (size_t)(h - out_row0) * GRID_COLS;
         for (int k = lt; k < GRID_COLS; k += SP_NT) {
-            const float2 zk = buf[k];
-            const float2 zm = buf[k == 0 ? 0 : 1920 - k];
+            const int km = (k == 0) ? 0 : 1920 - k;
+            const float2 zk = buf[k + k / 120];                     // padded layout
+            const float2 zm = buf[km + km / 120];
             // e = (zk + conj(zm))/2,  o = -i/2 * (zk - conj(zm)) = (0.5 (zk.y + zm.y), -0.5 (zk.x - zm.x))
             const float2 e = cscale(0.5f, cfma_elem(zm, 1.0f, -1.0f, zk));
             const float2 dz = cfma_elem(zm, -1.0f, 1.0f, zk);
