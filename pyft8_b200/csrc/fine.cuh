@@ -144,54 +144,13 @@ struct FineOut {               // per candidate
     int32_t snr;
 };
 
-// Inverse 3200-point FFT of the tapered band around fb (receiver.py:180-186), result in `dst`, `tmp` is scratch.
+// Inverse 3200-point FFT of the tapered band around fb (receiver.py:180-186).
 // Band layout after the reference's roll(-150): a[i] = spec[fb + i] for i < 850 (taper on [750,850)),
 // spec[fb + i - 3200] for i >= 3050 (taper on [3050,3150)), zero elsewhere.  First pass (R=5, S=1, M=640) reads the
 // operands a[p + 640 j] straight from the spectrum: j = 2, 3 are always zero, j = 1 is non-zero only for p < 210 and
 // j = 4 only for p >= 490, so the radix-5 butterfly degenerates to b_k = a0 + a1 w^k + a4 conj(w^k), w = e^{+2 pi i/5}.
-__device__ __forceinline__ void fine_pass1(float2* tmp, const float2* __restrict__ spec, int fb, int tid,
-                                           const float2* __restrict__ TF, const float* taper) {
-    constexpr int NBF = 640;
-#pragma unroll
-    for (int p0 = 0; p0 < NBF; p0 += FINE_NT) {
-        const int p = p0 + tid;
-        if (p < NBF) {
-            float2 a0 = __ldg(&spec[fb + p]);                       // i = p < 640: inside [0,850), taper-free
-            float2 b[5] = {a0, a0, a0, a0, a0};
-            if (p < 210) {                                          // i = p + 640 in [640, 850)
-                float2 a1 = __ldg(&spec[fb + p + 640]);
-                if (p >= 110) a1 = cscale(taper[p - 110], a1);
-                const float2 w1 = make_float2(0.30901699437494742410f, 0.95105651629515357212f);
-                const float2 w2 = make_float2(-0.80901699437494742410f, 0.58778525229247312917f);
-                b[0] = cadd(a0, a1);
-                b[1] = cadd(a0, cmul(a1, w1));
-                b[2] = cadd(a0, cmul(a1, w2));
-                b[3] = cadd(a0, cmulc(a1, w2));
-                b[4] = cadd(a0, cmulc(a1, w1));
-            } else if (p >= 490) {                                  // i = p + 2560 in [3050, 3200)
-                float2 a4 = __ldg(&spec[fb + p - 640]);
-                if (p < 590) a4 = cscale(taper[p - 490], a4);
-                const float2 w1 = make_float2(0.30901699437494742410f, 0.95105651629515357212f);
-                const float2 w2 = make_float2(-0.80901699437494742410f, 0.58778525229247312917f);
-                b[0] = cadd(a0, a4);
-                b[1] = cadd(a0, cmulc(a4, w1));
-                b[2] = cadd(a0, cmulc(a4, w2));
-                b[3] = cadd(a0, cmul(a4, w2));
-                b[4] = cadd(a0, cmul(a4, w1));
-            }
-            tmp[5 * p] = b[0];
-#pragma unroll
-            for (int k = 1; k < 5; ++k) tmp[5 * p + k] = cmulc(b[k], __ldg(&TF[(k - 1) * NBF + p]));     // = W3200[p k], stored [k-1][p]
-        }
-    }
-}
-
-// passes (5,5) (8,25): a -> b -> a, one barrier after each; `a` then holds the operands of the last pass (16,200)
+// Per-pass twiddle tables in TF ([k-1][p] layout): first pass 4 x 640 | (5,5) 4 x 128 | (8,25) 7 x 16.
 constexpr int FINE_T5_OFF = 4 * 640, FINE_T8_OFF = FINE_T5_OFF + 4 * 128, FINE_TF_LEN = FINE_T8_OFF + 7 * 16;
-__device__ __forceinline__ void fine_pass23(float2* a, float2* b, int tid, const float2* __restrict__ TF) {
-    pass_oop<3200, 5, 5, FINE_NT, true, true, true>(a, b, tid, TF + FINE_T5_OFF);    // p-major: stride-5 loads, stride-25 stores
-    pass_oop<3200, 8, 25, FINE_NT, true, true>(b, a, tid, TF + FINE_T8_OFF);
-}
 
 // Passes (5,1) and (5,5) fused, one thread per p2 < 128 (four warps): the thread builds the five sparse first-pass
 // butterflies p = p2 + 128 j in registers (25 values, same arithmetic as fine_pass1), then runs the five second-pass
