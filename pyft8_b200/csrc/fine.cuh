@@ -87,7 +87,7 @@ k_cs_cols(const T* __restrict__ audio, float2* __restrict__ Y, const float2* __r
 }
 
 constexpr int CSR_G = 8;      // k1 values per CTA (plus their mirrors)
-constexpr int CSR_STRIDE = CS_N2 + CS_N2 / 16;
+constexpr int CSR_STRIDE = CS_N2 + CS_N2 / 16 + 4;   // 276: row stride = 4 (mod 16) 8-byte banks, so the untangle's 8-row gathers are conflict-free
 // grid (24, B): k1 in {0} u [1,187] in groups of 8.  spec: [B][spec_stride] float2, bins <= kmax written.
 __global__ void __launch_bounds__(CS_NT)
 k_cs_rows(const float2* __restrict__ Y, float2* __restrict__ spec, int spec_stride, int kmax,
