@@ -158,18 +158,31 @@ constexpr int FINE_T5_OFF = 4 * 640, FINE_T8_OFF = FINE_T5_OFF + 4 * 128, FINE_T
 // conflict).  Against the two separate passes this drops the 3200-element store + reload of the intermediate and 16 of the
 // 20 second-pass twiddle loads per p2 -- about 30 % of the kernel's traffic on the shared-memory / L1 pipe, which is what
 // bounds it -- and needs no shared-memory input, so the other four warps can score the previous transform meanwhile.
-__device__ __forceinline__ void fine_pass12(float2* dst, const float2* __restrict__ spec, int fb, int p2,
-                                            const float2* __restrict__ TF, const float* taper) {
+// The spectrum reads of a fused transform come from L2 (several hundred cycles): they are issued one barrier phase early
+// (fine_pass12_load, before pass (8,25) of the transform in flight) and consumed after it (fine_pass12_finish).
+struct FineIn { float2 a0[5]; float2 ax[4]; };    // ax: the second non-zero operand of butterflies j = 0, 1 (a1) and 3, 4 (a4)
+
+__device__ __forceinline__ void fine_pass12_load(FineIn& in, const float2* __restrict__ spec, int fb, int p2) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) in.a0[j] = __ldg(&spec[fb + p2 + 128 * j]);
+    in.ax[0] = __ldg(&spec[fb + p2 + 640]);                                  // j = 0: p = p2 < 210 always
+    in.ax[1] = (p2 + 128 < 210) ? __ldg(&spec[fb + p2 + 128 + 640]) : make_float2(0.f, 0.f);
+    in.ax[2] = (p2 + 384 >= 490) ? __ldg(&spec[fb + p2 + 384 - 640]) : make_float2(0.f, 0.f);
+    in.ax[3] = __ldg(&spec[fb + p2 + 512 - 640]);                            // j = 4: p >= 512 always
+}
+
+__device__ __forceinline__ void fine_pass12_finish(const FineIn& in, float2* dst, int p2, const float2* __restrict__ TF,
+                                                   const float* taper) {
     float2 x[5][5];                                                 // x[j][k]: output k of first-pass butterfly p2 + 128 j
     const float2 w1 = make_float2(0.30901699437494742410f, 0.95105651629515357212f);
     const float2 w2 = make_float2(-0.80901699437494742410f, 0.58778525229247312917f);
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int p = p2 + 128 * j;
-        const float2 a0 = __ldg(&spec[fb + p]);
+        const float2 a0 = in.a0[j];
         float2 b[5] = {a0, a0, a0, a0, a0};
         if (j < 2 && p < 210) {                                     // i = p + 640 in [640, 850)
-            float2 a1 = __ldg(&spec[fb + p + 640]);
+            float2 a1 = in.ax[j];
             if (p >= 110) a1 = cscale(taper[p - 110], a1);
             b[0] = cadd(a0, a1);
             b[1] = cadd(a0, cmul(a1, w1));
@@ -177,7 +190,7 @@ __device__ __forceinline__ void fine_pass12(float2* dst, const float2* __restric
             b[3] = cadd(a0, cmulc(a1, w2));
             b[4] = cadd(a0, cmulc(a1, w1));
         } else if (j > 2 && p >= 490) {                             // i = p + 2560 in [3050, 3200)
-            float2 a4 = __ldg(&spec[fb + p - 640]);
+            float2 a4 = in.ax[j - 1];
             if (p < 590) a4 = cscale(taper[p - 490], a4);
             b[0] = cadd(a0, a4);
             b[1] = cadd(a0, cmulc(a4, w1));
@@ -200,6 +213,13 @@ __device__ __forceinline__ void fine_pass12(float2* dst, const float2* __restric
 #pragma unroll
         for (int k = 1; k < 5; ++k) dst[q + 25 * p2 + 5 * k] = cmulc(a[k], w[k - 1]);
     }
+}
+
+__device__ __forceinline__ void fine_pass12(float2* dst, const float2* __restrict__ spec, int fb, int p2,
+                                            const float2* __restrict__ TF, const float* taper) {
+    FineIn in;
+    fine_pass12_load(in, spec, fb, p2);
+    fine_pass12_finish(in, dst, p2, TF, taper);
 }
 
 // Pass (8,25) px -> po by all 256 threads; output in the padded operand layout: element q + 25 (8 p + k) goes to
@@ -364,6 +384,8 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         // ---- time scan at ftweak = 0 (receiver.py:147-152): 8 window starts share one inverse FFT.
         //      Middle-Costas windows start at tb0 + tt + 32*(36+k) in [849, 2082] for every reachable h0: never clipped.
         //      px already holds the fused first passes of this item's ftweak = 0 transform.
+        FineIn fin;
+        if (warp >= 4) fine_pass12_load(fin, sp, fb0 - 32, tid - 128);       // operands of the next transform: in flight during pass (8,25)
         fine_pass3(px, po, tid, TF);
         if (warp < 4) {
             fine_pass4_window(po, zwin, tb0 - 8 + 1152, 238, tid, w16);
@@ -376,7 +398,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
                 if (lane == 0) score[st] = sc;
             }
         } else {
-            fine_pass12(px, sp, fb0 - 32, tid - 128, TF, taper);     // first frequency tweak, built during the time scan
+            fine_pass12_finish(fin, px, tid - 128, TF, taper);        // first frequency tweak, built during the time scan
         }
         __syncthreads();
         int tt = -8;
@@ -389,6 +411,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         int best_fi = 4;
         for (int e = 0; e < 8; ++e) {
             const int fi = e < 4 ? e : e + 1;
+            if (warp >= 4 && e < 7) fine_pass12_load(fin, sp, fb0 + (-32 + 8 * (e + 1 < 4 ? e + 1 : e + 2)), tid - 128);
             fine_pass3(px, po, tid, TF);
             if (warp < 4) {
                 fine_pass4_window(po, zwin, tb0 + tt + 1152, 224, tid, w16);
@@ -398,7 +421,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
                     if (lane == 0) score[8 + warp] = r;
                 }
             } else if (e < 7) {
-                fine_pass12(px, sp, fb0 + (-32 + 8 * (e + 1 < 4 ? e + 1 : e + 2)), tid - 128, TF, taper);
+                fine_pass12_finish(fin, px, tid - 128, TF, taper);
             }
             __syncthreads();
             const float sc = score[8] + score[9];
