@@ -171,48 +171,53 @@ __device__ __forceinline__ void fine_pass12_load(FineIn& in, const float2* __res
     in.ax[3] = __ldg(&spec[fb + p2 + 512 - 640]);                            // j = 4: p >= 512 always
 }
 
-__device__ __forceinline__ void fine_pass12_finish(const FineIn& in, float2* dst, int p2, const float2* __restrict__ TF,
-                                                   const float* taper) {
-    float2 x[5][5];                                                 // x[j][k]: output k of first-pass butterfly p2 + 128 j
+// First-pass output q of sparse butterfly with second operand a1 (at j = 1) / a4 (at j = 4): b_q = a0 + a1 w^q, a0 + a4 conj(w^q)
+template <int Q, bool A4> __device__ __forceinline__ float2 fine_b(float2 a0, float2 ax) {
     const float2 w1 = make_float2(0.30901699437494742410f, 0.95105651629515357212f);
     const float2 w2 = make_float2(-0.80901699437494742410f, 0.58778525229247312917f);
+    if (Q == 0) return cadd(a0, ax);
+    const float2 w = (Q == 1 || Q == 4) ? w1 : w2;
+    const bool conj = (Q >= 3) != A4;                     // a1 form: conj for q = 3, 4; a4 form: conj for q = 1, 2
+    return cadd(a0, conj ? cmulc(ax, w) : cmul(ax, w));
+}
+
+// One column q at a time (the five first-pass outputs q, then second-pass butterfly (p2, q)): same arithmetic as building
+// all 25 first-pass outputs first, but ~40 live registers instead of ~90, which is what lets three CTAs share an SM.
+template <int Q>
+__device__ __forceinline__ void fine_pass12_col(const FineIn& in, const float2 (&ax)[4], float2* dst, int p2,
+                                                const float2* __restrict__ TF, const float2 (&w)[4]) {
+    float2 a[5];
+    a[0] = fine_b<Q, false>(in.a0[0], ax[0]);
+    a[1] = (p2 < 82) ? fine_b<Q, false>(in.a0[1], ax[1]) : in.a0[1];
+    a[2] = in.a0[2];
+    a[3] = (p2 >= 106) ? fine_b<Q, true>(in.a0[3], ax[2]) : in.a0[3];
+    a[4] = fine_b<Q, true>(in.a0[4], ax[3]);
+    if (Q > 0) {
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const int p = p2 + 128 * j;
-        const float2 a0 = in.a0[j];
-        float2 b[5] = {a0, a0, a0, a0, a0};
-        if (j < 2 && p < 210) {                                     // i = p + 640 in [640, 850)
-            float2 a1 = in.ax[j];
-            if (p >= 110) a1 = cscale(taper[p - 110], a1);
-            b[0] = cadd(a0, a1);
-            b[1] = cadd(a0, cmul(a1, w1));
-            b[2] = cadd(a0, cmul(a1, w2));
-            b[3] = cadd(a0, cmulc(a1, w2));
-            b[4] = cadd(a0, cmulc(a1, w1));
-        } else if (j > 2 && p >= 490) {                             // i = p + 2560 in [3050, 3200)
-            float2 a4 = in.ax[j - 1];
-            if (p < 590) a4 = cscale(taper[p - 490], a4);
-            b[0] = cadd(a0, a4);
-            b[1] = cadd(a0, cmulc(a4, w1));
-            b[2] = cadd(a0, cmulc(a4, w2));
-            b[3] = cadd(a0, cmul(a4, w2));
-            b[4] = cadd(a0, cmul(a4, w1));
-        }
-        x[j][0] = b[0];
-#pragma unroll
-        for (int k = 1; k < 5; ++k) x[j][k] = cmulc(b[k], __ldg(&TF[(k - 1) * 640 + p]));
+        for (int j = 0; j < 5; ++j) a[j] = cmulc(a[j], __ldg(&TF[(Q - 1) * 640 + p2 + 128 * j]));
     }
+    Dft<5, true>::run(a);
+    dst[Q + 25 * p2] = a[0];
+#pragma unroll
+    for (int k = 1; k < 5; ++k) dst[Q + 25 * p2 + 5 * k] = cmulc(a[k], w[k - 1]);
+}
+
+__device__ __forceinline__ void fine_pass12_finish(const FineIn& in, float2* dst, int p2, const float2* __restrict__ TF,
+                                                   const float* taper) {
+    // tapered edge operands (receiver.py:182-183): a1 of p = p2 (>= 110) and p2 + 128; a4 of p2 + 384 and p2 + 512 (< 590)
+    float2 ax[4] = {in.ax[0], in.ax[1], in.ax[2], in.ax[3]};
+    if (p2 >= 110) ax[0] = cscale(taper[p2 - 110], ax[0]);
+    if (p2 < 82) ax[1] = cscale(taper[p2 + 18], ax[1]);
+    if (p2 >= 106) ax[2] = cscale(taper[p2 - 106], ax[2]);
+    if (p2 < 78) ax[3] = cscale(taper[p2 + 22], ax[3]);
     float2 w[4];
 #pragma unroll
     for (int k = 1; k < 5; ++k) w[k - 1] = __ldg(&TF[FINE_T5_OFF + (k - 1) * 128 + p2]);
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        float2 a[5] = {x[0][q], x[1][q], x[2][q], x[3][q], x[4][q]};
-        Dft<5, true>::run(a);
-        dst[q + 25 * p2] = a[0];
-#pragma unroll
-        for (int k = 1; k < 5; ++k) dst[q + 25 * p2 + 5 * k] = cmulc(a[k], w[k - 1]);
-    }
+    fine_pass12_col<0>(in, ax, dst, p2, TF, w);
+    fine_pass12_col<1>(in, ax, dst, p2, TF, w);
+    fine_pass12_col<2>(in, ax, dst, p2, TF, w);
+    fine_pass12_col<3>(in, ax, dst, p2, TF, w);
+    fine_pass12_col<4>(in, ax, dst, p2, TF, w);
 }
 
 __device__ __forceinline__ void fine_pass12(float2* dst, const float2* __restrict__ spec, int fb, int p2,
