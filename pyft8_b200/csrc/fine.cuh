@@ -227,22 +227,24 @@ __device__ __forceinline__ void fine_pass12(float2* dst, const float2* __restric
     fine_pass12_finish(in, dst, p2, TF, taper);
 }
 
-// Pass (8,25) px -> po by all 256 threads; output in the padded operand layout: element q + 25 (8 p + k) goes to
-// q + 201 p + 25 k (q + 25 k < 200).  One barrier at the end.
-__device__ __forceinline__ void fine_pass3(const float2* src, float2* dst, int tid, const float2* __restrict__ TF) {
+// Pass (8,25) px -> po by all 256 threads, p-major: thread tid owns p = tid % 16 in both of its butterflies (q = tid / 16 and
+// tid / 16 + 16), so its 7 twiddles w^(25 p k) live in registers for the whole kernel (tw8, loaded once) -- no twiddle loads
+// in this pass at all.  Loads have stride 25 elements across lanes, stores go to the padded operand layout
+// q + 201 p + 25 k (stride 201): both conflict-free.  One barrier at the end.
+__device__ __forceinline__ void fine_pass3(const float2* src, float2* dst, int tid, const float2 (&tw8)[7]) {
+    const int p = tid & 15;
 #pragma unroll
-    for (int t0 = 0; t0 < 400; t0 += FINE_NT) {
-        const int t = t0 + tid;
-        if (t < 400) {
-            const int p = t / 25, q = t - 25 * p;
+    for (int r = 0; r < 2; ++r) {
+        const int q = (tid >> 4) + 16 * r;
+        if (q < 25) {
             float2 a[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = src[t + 400 * j];
+            for (int j = 0; j < 8; ++j) a[j] = src[q + 25 * p + 400 * j];
             Dft<8, true>::run(a);
             float2* d = dst + q + 201 * p;
             d[0] = a[0];
 #pragma unroll
-            for (int k = 1; k < 8; ++k) d[25 * k] = cmulc(a[k], __ldg(&TF[FINE_T8_OFF + (k - 1) * 16 + p]));
+            for (int k = 1; k < 8; ++k) d[25 * k] = cmulc(a[k], tw8[k - 1]);
         }
     }
     __syncthreads();
@@ -365,6 +367,9 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
     float2 tw[8];                                                     // this lane's DFT32 twiddles, fixed for the kernel
 #pragma unroll
     for (int t = 0; t < 8; ++t) tw[t] = w32[(t * (lane & 7)) & 31];
+    float2 tw8[7];                                                    // this thread's pass-(8,25) twiddles (p = tid % 16), fixed too
+#pragma unroll
+    for (int k = 1; k < 8; ++k) tw8[k - 1] = __ldg(&TF[FINE_T8_OFF + (k - 1) * 16 + (tid & 15)]);
     const int n_items = list ? *count : n_direct;
     // the first transform of the CTA's first item; every later item's first transform is built by the producer warps
     // during the final stage of the item before it
@@ -391,7 +396,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         //      px already holds the fused first passes of this item's ftweak = 0 transform.
         FineIn fin;
         if (warp >= 4) fine_pass12_load(fin, sp, fb0 - 32, tid - 128);       // operands of the next transform: in flight during pass (8,25)
-        fine_pass3(px, po, tid, TF);
+        fine_pass3(px, po, tid, tw8);
         if (warp < 4) {
             fine_pass4_window(po, zwin, tb0 - 8 + 1152, 238, tid, w16);
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -417,7 +422,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         for (int e = 0; e < 8; ++e) {
             const int fi = e < 4 ? e : e + 1;
             if (warp >= 4 && e < 7) fine_pass12_load(fin, sp, fb0 + (-32 + 8 * (e + 1 < 4 ? e + 1 : e + 2)), tid - 128);
-            fine_pass3(px, po, tid, TF);
+            fine_pass3(px, po, tid, tw8);
             if (warp < 4) {
                 fine_pass4_window(po, zwin, tb0 + tt + 1152, 224, tid, w16);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
