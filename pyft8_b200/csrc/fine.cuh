@@ -185,7 +185,7 @@ template <int Q, bool A4> __device__ __forceinline__ float2 fine_b(float2 a0, fl
 // all 25 first-pass outputs first, but ~40 live registers instead of ~90, which is what lets three CTAs share an SM.
 template <int Q>
 __device__ __forceinline__ void fine_pass12_col(const FineIn& in, const float2 (&ax)[4], float2* dst, int p2,
-                                                const float2* __restrict__ TF, const float2 (&w)[4]) {
+                                                const float2* __restrict__ TF, const float2 (&w)[8]) {
     float2 a[5];
     a[0] = fine_b<Q, false>(in.a0[0], ax[0]);
     a[1] = (p2 < 82) ? fine_b<Q, false>(in.a0[1], ax[1]) : in.a0[1];
@@ -202,17 +202,15 @@ __device__ __forceinline__ void fine_pass12_col(const FineIn& in, const float2 (
     for (int k = 1; k < 5; ++k) dst[Q + 25 * p2 + 5 * k] = cmulc(a[k], w[k - 1]);
 }
 
+// w5[0..3]: the thread's second-pass twiddles w^(5 p2 k), k = 1..4 (held in registers by the producer warps)
 __device__ __forceinline__ void fine_pass12_finish(const FineIn& in, float2* dst, int p2, const float2* __restrict__ TF,
-                                                   const float* taper) {
+                                                   const float* taper, const float2 (&w)[8]) {
     // tapered edge operands (receiver.py:182-183): a1 of p = p2 (>= 110) and p2 + 128; a4 of p2 + 384 and p2 + 512 (< 590)
     float2 ax[4] = {in.ax[0], in.ax[1], in.ax[2], in.ax[3]};
     if (p2 >= 110) ax[0] = cscale(taper[p2 - 110], ax[0]);
     if (p2 < 82) ax[1] = cscale(taper[p2 + 18], ax[1]);
     if (p2 >= 106) ax[2] = cscale(taper[p2 - 106], ax[2]);
     if (p2 < 78) ax[3] = cscale(taper[p2 + 22], ax[3]);
-    float2 w[4];
-#pragma unroll
-    for (int k = 1; k < 5; ++k) w[k - 1] = __ldg(&TF[FINE_T5_OFF + (k - 1) * 128 + p2]);
     fine_pass12_col<0>(in, ax, dst, p2, TF, w);
     fine_pass12_col<1>(in, ax, dst, p2, TF, w);
     fine_pass12_col<2>(in, ax, dst, p2, TF, w);
@@ -221,10 +219,10 @@ __device__ __forceinline__ void fine_pass12_finish(const FineIn& in, float2* dst
 }
 
 __device__ __forceinline__ void fine_pass12(float2* dst, const float2* __restrict__ spec, int fb, int p2,
-                                            const float2* __restrict__ TF, const float* taper) {
+                                            const float2* __restrict__ TF, const float* taper, const float2 (&w)[8]) {
     FineIn in;
     fine_pass12_load(in, spec, fb, p2);
-    fine_pass12_finish(in, dst, p2, TF, taper);
+    fine_pass12_finish(in, dst, p2, TF, taper, w);
 }
 
 // Pass (8,25) px -> po by all 256 threads, p-major: thread tid owns p = tid % 16 in both of its butterflies (q = tid / 16 and
@@ -367,6 +365,11 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
     float2 tw[8];                                                     // this lane's DFT32 twiddles, fixed for the kernel
 #pragma unroll
     for (int t = 0; t < 8; ++t) tw[t] = w32[(t * (lane & 7)) & 31];
+    // the producer warps never run symbol DFTs: their tw[0..3] hold the second-pass twiddles of p2 = tid - 128 instead
+    if (warp >= 4) {
+#pragma unroll
+        for (int k = 1; k < 5; ++k) tw[k - 1] = __ldg(&TF[FINE_T5_OFF + (k - 1) * 128 + (tid - 128)]);
+    }
     float2 tw8[7];                                                    // this thread's pass-(8,25) twiddles (p = tid % 16), fixed too
 #pragma unroll
     for (int k = 1; k < 8; ++k) tw8[k - 1] = __ldg(&TF[FINE_T8_OFF + (k - 1) * 16 + (tid & 15)]);
@@ -375,7 +378,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
     // during the final stage of the item before it
     if (warp >= 4 && (int)blockIdx.x < n_items) {
         const int slot = list ? list[blockIdx.x] : (int)blockIdx.x;
-        fine_pass12(fine_smem, spec + (size_t)cycle_of[slot] * spec_stride, 50 * cand_f0[slot], tid - 128, TF, taper);
+        fine_pass12(fine_smem, spec + (size_t)cycle_of[slot] * spec_stride, 50 * cand_f0[slot], tid - 128, TF, taper, tw);
     }
     __syncthreads();
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -408,7 +411,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
                 if (lane == 0) score[st] = sc;
             }
         } else {
-            fine_pass12_finish(fin, px, tid - 128, TF, taper);        // first frequency tweak, built during the time scan
+            fine_pass12_finish(fin, px, tid - 128, TF, taper, tw);        // first frequency tweak, built during the time scan
         }
         __syncthreads();
         int tt = -8;
@@ -431,7 +434,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
                     if (lane == 0) score[8 + warp] = r;
                 }
             } else if (e < 7) {
-                fine_pass12_finish(fin, px, tid - 128, TF, taper);
+                fine_pass12_finish(fin, px, tid - 128, TF, taper, tw);
             }
             __syncthreads();
             const float sc = score[8] + score[9];
@@ -482,7 +485,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
             const int nitem = item + gridDim.x;
             if (nitem < n_items) {
                 const int nslot = list ? list[nitem] : nitem;
-                fine_pass12(px, spec + (size_t)cycle_of[nslot] * spec_stride, 50 * cand_f0[nslot], tid - 128, TF, taper);
+                fine_pass12(px, spec + (size_t)cycle_of[nslot] * spec_stride, 50 * cand_f0[nslot], tid - 128, TF, taper, tw);
             }
         }
         __syncthreads();
