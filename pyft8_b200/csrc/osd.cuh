@@ -38,7 +38,17 @@ struct OsdWarpScratch {
 
 // Returns trial index + 1 of the first accepted trial word (0 = none); bits = that word.
 // llr: 174 floats in shared or global memory.
-__device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int lane, const LaneSyn& ls, int S, int D, uint32_t* bits) {
+// CTA-shared copy of the generator columns, word-major [3][176]: after the sort every lane asks for a different column, and
+// a lane-indexed read of __constant__ memory is replayed once per distinct address (up to 32 times per load).
+constexpr int OSD_COL_PITCH = 176;
+struct OsdCtaTables { uint32_t col[3 * OSD_COL_PITCH]; };
+__device__ __forceinline__ void load_osd_tables(OsdCtaTables& t) {
+    for (int i = threadIdx.x; i < 174; i += blockDim.x) {
+        t.col[i] = c_osd.col[i][0]; t.col[OSD_COL_PITCH + i] = c_osd.col[i][1]; t.col[2 * OSD_COL_PITCH + i] = c_osd.col[i][2];
+    }
+}
+
+__device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g, const float* llr, int lane, const LaneSyn& ls, int S, int D, uint32_t* bits) {
     // ---- 1. reliability order: bitonic sort of 256 64-bit keys (8 per lane, slot e = 32*r + lane), descending.
     //      key = (|llr| bits + 1, or 0 for NaN) << 8 | (255 - index): larger |llr| first, ties by ascending index, NaN after
     //      every number, the 82 padding slots (key 0) last.  Slot e ends up holding the e-th column in reliability order.
@@ -95,7 +105,7 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const float* llr, int
         if (sp < 174) {
             const int c = 255 - (int)(key[r] & 0xFFull);
             orig[r] = c;
-            c0[r] = c_osd.col[c][0]; c1[r] = c_osd.col[c][1]; c2[r] = c_osd.col[c][2];
+            c0[r] = g.col[c]; c1[r] = g.col[OSD_COL_PITCH + c]; c2[r] = g.col[2 * OSD_COL_PITCH + c];
             if (llr[c] > 0.0f) hard_mask |= 1u << r;
         } else {
             orig[r] = 255; c0[r] = c1[r] = c2[r] = 0;

@@ -246,6 +246,7 @@ k_pass234(CandState cs, const int32_t* __restrict__ list, const int32_t* __restr
 }
 
 struct OsdSmem {
+    OsdCtaTables tab;
     OsdWarpScratch w[WARPS_PER_CTA];
     float llr[WARPS_PER_CTA][176];
 };
@@ -258,6 +259,8 @@ k_osd_items(CandState cs, const int32_t* __restrict__ list, const int32_t* __res
     OsdSmem& sm = *reinterpret_cast<OsdSmem*>(pass_smem_raw);
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const LaneSyn ls = load_lane_syn(lane);
+    load_osd_tables(sm.tab);
+    __syncthreads();
     const int warps_total = gridDim.x * WARPS_PER_CTA;
     const int n_items = *count * 10;
     unsigned long long n_osd = 0;
@@ -275,7 +278,7 @@ k_osd_items(CandState cs, const int32_t* __restrict__ list, const int32_t* __res
             // attempts 0..4: Candidate._set_AP pattern on the fine llr; 5..9: llr saved after a failed LDPC(90,20)
             const float* src = (k < 5) ? cs.llr_fine + (size_t)slot * 174 : cs.saved_llr + ((size_t)slot * 5 + (k - 5)) * 174;
             apply_ap(sm.llr[wi], src, (k < 5) ? k : 0, lane);
-            found = osd_warp(sm.w[wi], sm.llr[wi], lane, ls, S, D, bits);
+            found = osd_warp(sm.w[wi], sm.tab, sm.llr[wi], lane, ls, S, D, bits);
             ++n_osd;
         }
         if (lane == 0) {
@@ -356,11 +359,13 @@ k_osd_batch(const float* __restrict__ llr, int N, int S, int D, int32_t* __restr
     OsdSmem& sm = *reinterpret_cast<OsdSmem*>(pass_smem_raw);
     const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const LaneSyn ls = load_lane_syn(lane);
+    load_osd_tables(sm.tab);
+    __syncthreads();
     for (int n = blockIdx.x * WARPS_PER_CTA + wi; n < N; n += gridDim.x * WARPS_PER_CTA) {
         for (int i = lane; i < 174; i += 32) sm.llr[wi][i] = llr[(size_t)n * 174 + i];
         __syncwarp();
         uint32_t bits[3];
-        const int f = osd_warp(sm.w[wi], sm.llr[wi], lane, ls, S, D, bits);
+        const int f = osd_warp(sm.w[wi], sm.tab, sm.llr[wi], lane, ls, S, D, bits);
         if (lane == 0) { found[n] = f; bits_out[3 * n] = bits[0]; bits_out[3 * n + 1] = bits[1]; bits_out[3 * n + 2] = bits[2]; }
         __syncwarp();
     }
