@@ -469,7 +469,7 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
                 if (lane < 29) {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        const int sym = c_payload_sym[lane + 29 * q];
+                        const int sym = lane + (q ? 43 : 7);                  // PAYLOAD_SYMB_IDXS = 7..35, 43..71
 #pragma unroll
                         for (int t = 0; t < 8; ++t) p[q][t] = 20.0f * log10f(G[sym * 8 + t]);
                     }

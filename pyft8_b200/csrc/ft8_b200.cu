@@ -170,7 +170,7 @@ static cudaError_t upload_constant_tables() {
     for (int a = 0; a < 5; ++a) {
         ap.first[a] = (int8_t)first[a];
         ap.len[a] = (int8_t)strlen(pat[a]);
-        for (int i = 0; i < ap.len[a]; ++i) ap.bits[a][i] = pat[a][i] == '1';
+        for (int i = 0; i < ap.len[a]; ++i) if (pat[a][i] == '1') ap.mask[a] |= 1u << i;
     }
     e = cudaMemcpyToSymbol(c_ap, &ap, sizeof(ap));
     if (e != cudaSuccess) return e;

@@ -26,7 +26,8 @@ constexpr int WARPS_PER_CTA = 4;
 struct ApTables {
     int8_t first[5];          // first llr index of the pattern
     int8_t len[5];
-    int8_t bits[5][32];       // 0/1
+    uint32_t mask[5];         // bit i = i-th forced bit (a word per pattern: a lane-indexed byte table in __constant__
+                              // memory would be replayed once per lane)
 };
 __constant__ ApTables c_ap;
 
@@ -36,7 +37,7 @@ __device__ __forceinline__ void apply_ap(float* dst, const float* src, int ap, i
     for (int i = lane; i < 174; i += 32) dst[i] = src[i];
     __syncwarp();
     if (ap > 0) {
-        if (lane < c_ap.len[ap]) dst[c_ap.first[ap] + lane] = c_ap.bits[ap][lane] ? 5.0f : -5.0f;
+        if (lane < c_ap.len[ap]) dst[c_ap.first[ap] + lane] = ((c_ap.mask[ap] >> lane) & 1u) ? 5.0f : -5.0f;
         if (ap == 1 && lane == 0) { dst[74] = -5.0f; dst[75] = -5.0f; dst[76] = 5.0f; dst[57] = -5.0f; dst[58] = -5.0f; }
     }
     __syncwarp();
@@ -120,7 +121,7 @@ k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows
         if (lane < 29) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const int sym = c_payload_sym[lane + 29 * q];
+                const int sym = lane + (q ? 43 : 7);                  // PAYLOAD_SYMB_IDXS = 7..35, 43..71
                 const int row = cycle_h0 + h0 + 4 + 4 * sym;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {

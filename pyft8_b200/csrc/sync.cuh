@@ -22,10 +22,7 @@ constexpr int SY_NT = 256;
 constexpr int LIVE_ROWS = 750;
 
 __constant__ int c_costas[7] = {3, 1, 4, 0, 6, 5, 2};
-__constant__ uint8_t c_payload_sym[58] = {7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27,
-                                           28, 29, 30, 31, 32, 33, 34, 35, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54,
-                                           55, 56, 57, 58, 59, 60, 61, 62, 63, 64, 65, 66, 67, 68, 69, 70, 71};
-
+// payload symbol s' (0..57) sits at Costas-framed symbol s' + 7 (first half) or s' + 14 (second half): 7..35, 43..71
 // grid value with the reference's ring semantics: row index taken mod 750; rows that are not stored hold 1.0
 __device__ __forceinline__ float grid_at(const float* g, int grid_rows, int row, int col) {
     row %= LIVE_ROWS;
