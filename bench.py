@@ -36,17 +36,17 @@ ALG_BYTES = {
     "osd": 696 + 64,                                # per OSD call
 }
 # measured DRAM traffic per cycle (bytes) of each stage's kernels: dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture at 4096 cycles/launch, divided by 4096 (profiles/r01h_summary.md; osd from the earlier r01e capture, its kernel is unchanged)
-NCU_DRAM_BYTES_PER_CYCLE = {"spectrogram": (1475e6 + 5959e6) / 4096, "sync": (2328e6 + 49e6 + 46e6) / 4096, "fine": (2889e6 + 492e6) / 4096,
-                            "pass0_ldpc5": (3723e6 + 615e6) / 4096, "osd": (541e6 + 25e6) / 4096,
+# `ncu --set full` capture at 4096 cycles/launch, divided by 4096 (profiles/r01i_summary.md; osd from the earlier r01e capture, its kernel is unchanged)
+NCU_DRAM_BYTES_PER_CYCLE = {"spectrogram": (1477e6 + 5959e6) / 4096, "sync": (2328e6 + 49e6 + 46e6) / 4096, "fine": (2892e6 + 492e6) / 4096,
+                            "pass0_ldpc5": (3733e6 + 616e6) / 4096, "osd": (541e6 + 25e6) / 4096,
                             "cycle_spectrum": (787e6 + 370e6 + 369e6 + 732e6) / 1024}
 # issue-slot / pipe utilisation of the same captures (percent of peak): what actually bounds the non-HBM stages.
 # l1_data_pipe = l1tex__data_pipe_lsu_wavefronts (shared-memory + L1 wavefronts): the binding resource of the FFT kernels.
-NCU_PIPES = {"spectrogram": {"issue_active": 72.2, "fma_pipe": 31.6, "alu_pipe": 37.7, "l1_data_pipe": 86.3},
-             "sync": {"issue_active": 74.9, "fma_pipe": 25.8, "alu_pipe": 43.2, "l1_data_pipe": 85.6},
-             "cycle_spectrum": {"issue_active": 39.6, "fma_pipe": 14.3, "alu_pipe": 26.9, "l1_data_pipe": 92.1},
-             "fine": {"issue_active": 42.4, "fma_pipe": 20.8, "alu_pipe": 17.5, "l1_data_pipe": 67.8},
-             "pass0_ldpc5": {"issue_active": 55.7, "fma_pipe": 21.2, "alu_pipe": 23.3, "l1_data_pipe": 70.4},
+NCU_PIPES = {"spectrogram": {"issue_active": 72.3, "fma_pipe": 31.7, "alu_pipe": 37.7, "l1_data_pipe": 86.4},
+             "sync": {"issue_active": 75.2, "fma_pipe": 25.9, "alu_pipe": 43.4, "l1_data_pipe": 85.9},
+             "cycle_spectrum": {"issue_active": 45.1, "fma_pipe": 16.4, "alu_pipe": 30.7, "l1_data_pipe": 88.3},
+             "fine": {"issue_active": 48.0, "fma_pipe": 22.9, "alu_pipe": 19.8, "l1_data_pipe": 64.0},
+             "pass0_ldpc5": {"issue_active": 56.7, "fma_pipe": 21.4, "alu_pipe": 24.0, "l1_data_pipe": 71.1},
              "osd": {"issue_active": 67.2, "fma_pipe": 6.5, "alu_pipe": 84.1}}
 STAGES = ["all", "spectrogram", "sync", "cycle_spectrum", "pass0_ldpc5", "fine", "pass234_ldpc", "osd", "collect"]
 
