@@ -343,6 +343,15 @@ __device__ __forceinline__ float costas_rows4(const float2* z, int z0, int k0, i
 
 constexpr int FINE_SMEM_BYTES = (FINE_N + 2 * FINE_NP) * (int)sizeof(float2) + (79 * 8 + 16 + 100) * (int)sizeof(float) + (32 + 16 + 256) * (int)sizeof(float2);
 
+// Optional phase timing (-DFINE_PROFILE, tools/fine_phase_profile.py): clock64 sums per barrier phase of the frequency scan.
+#ifdef FINE_PROFILE
+__device__ unsigned long long g_fine_prof[16];
+#define FP_T(v) const long long v = clock64()
+#define FP_ADD(i, d) do { if (lane == 0) atomicAdd(&g_fine_prof[i], (unsigned long long)(d)); } while (0)
+#else
+#define FP_T(v)
+#define FP_ADD(i, d)
+#endif
 // One CTA per work item (grid-stride over list[0..*count)).  cand arrays are indexed by the global slot id.
 // spec: [B][spec_stride] float2.  Outputs per slot: fo[slot], llr_fine[slot][174], optional sig_grid[slot][79][8].
 __global__ void __launch_bounds__(FINE_NT, 2)
@@ -425,18 +434,28 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         for (int e = 0; e < 8; ++e) {
             const int fi = e < 4 ? e : e + 1;
             if (warp >= 4 && e < 7) fine_pass12_load(fin, sp, fb0 + (-32 + 8 * (e + 1 < 4 ? e + 1 : e + 2)), tid - 128);
+            FP_T(t0);
             fine_pass3(px, po, tid, tw8);
+            FP_T(t1);
             if (warp < 4) {
                 fine_pass4_window(po, zwin, tb0 + tt + 1152, 224, tid, w16);
+                FP_T(tw0);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (warp < 2) {
                     const float r = costas_rows4(zwin, 0, 4 * warp, lane, tw);
                     if (lane == 0) score[8 + warp] = r;
                 }
+                FP_T(t2);
+                if (warp == 0) { FP_ADD(0, t1 - t0); FP_ADD(1, t2 - t1); FP_ADD(4, tw0 - t1); FP_ADD(6, 1); }
+                if (warp == 3) { FP_ADD(5, t2 - t1); }
             } else if (e < 7) {
                 fine_pass12_finish(fin, px, tid - 128, TF, taper, tw);
+                FP_T(t2);
+                if (warp == 4) { FP_ADD(2, t2 - t1); FP_ADD(7, 1); }
             }
             __syncthreads();
+            FP_T(t3);
+            if (warp == 0) FP_ADD(3, t3 - t1);
             const float sc = score[8] + score[9];
             if (sc > bestf || (sc == bestf && fi < best_fi)) { bestf = sc; best_fi = fi; float2* t = pb; pb = po; po = t; }
         }

@@ -1,4 +1,5 @@
 """Phase timing of k_fine (debug build with -DFINE_PROFILE): clock64 sums per barrier phase.
+   nvcc ... -DFINE_PROFILE -o build/variants/fineprof.so pyft8_b200/csrc/ft8_b200.cu
    PYFT8_B200_LIB=build/variants/fineprof.so python tools/fine_phase_profile.py"""
 import ctypes as C, os, sys
 import numpy as np, torch
