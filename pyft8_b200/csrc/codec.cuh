@@ -123,4 +123,9 @@ __device__ __forceinline__ bool payload_valid(const uint32_t* w) {
     return false;
 }
 
+// Out-of-line copy for the LDPC kernels: it runs only for the rare words whose CRC matches, and keeping its divisions out of
+// the belief-propagation loop keeps that loop's instruction-cache footprint small (k_pass0 5.97 -> 5.79 ms; the OSD kernel
+// is faster with the inlined form).
+__device__ __noinline__ bool payload_valid_cold(const uint32_t* w) { return payload_valid(w); }
+
 }  // namespace ft8
