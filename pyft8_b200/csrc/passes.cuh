@@ -213,21 +213,18 @@ k_pass234(CandState cs, const int32_t* __restrict__ list, const int32_t* __restr
                 done = true;
             }
         }
-        for (int ap = 0; ap < 2 && !done; ++ap) {             // ipass 3
-            apply_ap(ws.llr, llr0, ap, lane);
-            int nits, iters = 0;
-            const int st = ldpc_warp(ws, sm.tab, lane, ls, 35, 5, nits, bits, iters);
-            ++n_ldpc; n_iter += iters;
-            if (st == 1) { if (lane == 0) set_result(cs, slot, bits, 3, ap, 1, nits); done = true; }
-        }
+        // ipass 3 (two LDPC(35,5) attempts) and ipass 4 (five LDPC(90,20) attempts) share ONE inlined copy of the decoder
+        // (two call sites doubled the kernel's code and its instruction-fetch stalls)
         int nsaved = 0;
-        for (int ap = 0; ap < 5 && !done; ++ap) {             // ipass 4
+        for (int a = 0; a < 7 && !done; ++a) {
+            const bool p4 = a >= 2;
+            const int ap = p4 ? a - 2 : a;
             apply_ap(ws.llr, llr0, ap, lane);
             int nits, iters = 0;
-            const int st = ldpc_warp(ws, sm.tab, lane, ls, 90, 20, nits, bits, iters);
+            const int st = ldpc_warp(ws, sm.tab, lane, ls, p4 ? 90 : 35, p4 ? 20 : 5, nits, bits, iters);
             ++n_ldpc; n_iter += iters;
-            if (st == 1) { if (lane == 0) set_result(cs, slot, bits, 4, ap, 2, nits); done = true; }
-            else if (st >= 2) {                               // FAIL or STALL: reference keeps the llr (receiver.py:128-129)
+            if (st == 1) { if (lane == 0) set_result(cs, slot, bits, p4 ? 4 : 3, ap, p4 ? 2 : 1, nits); done = true; }
+            else if (p4 && st >= 2) {                         // FAIL or STALL: reference keeps the llr (receiver.py:128-129)
                 float* dst = cs.saved_llr + ((size_t)slot * 5 + nsaved) * 174;
                 for (int i = lane; i < 174; i += 32) dst[i] = ws.llr[i];
                 if (lane == 0) cs.saved_ap[slot * 5 + nsaved] = (uint8_t)ap;
