@@ -407,8 +407,10 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         //      Middle-Costas windows start at tb0 + tt + 32*(36+k) in [849, 2082] for every reachable h0: never clipped.
         //      px already holds the fused first passes of this item's ftweak = 0 transform.
         FineIn fin;
+        FP_T(ts0);
         if (warp >= 4) fine_pass12_load(fin, sp, fb0 - 32, tid - 128);       // operands of the next transform: in flight during pass (8,25)
         fine_pass3(px, po, tid, tw8);
+        FP_T(ts1);
         if (warp < 4) {
             fine_pass4_window(po, zwin, tb0 - 8 + 1152, 238, tid, w16);
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -419,8 +421,12 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
                 const float sc = costas_rows4(zwin, 2 * st, 0, lane, tw) + costas_rows4(zwin, 2 * st, 4, lane, tw);
                 if (lane == 0) score[st] = sc;
             }
+            FP_T(ts2);
+            if (warp == 0) { FP_ADD(8, ts1 - ts0); FP_ADD(9, ts2 - ts1); FP_ADD(11, 1); }
         } else {
             fine_pass12_finish(fin, px, tid - 128, TF, taper, tw);        // first frequency tweak, built during the time scan
+            FP_T(ts2);
+            if (warp == 4) FP_ADD(10, ts2 - ts1);
         }
         __syncthreads();
         int tt = -8;
@@ -463,7 +469,9 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
         // ---- full last pass of the winner, then the final grid (receiver.py:161) by the consumer warps (four symbol rows
         //      per warp and call) and the Costas count + LLRs by warp 0, while the producer warps already build the first
         //      transform of this CTA's next item into px (unused during this stage)
+        FP_T(tf0);
         fine_last_full(pb, po, tid);
+        FP_T(tf1);
         if (warp < 4) {
             const float2* z = po;
             for (int j0 = 4 * warp; j0 < 79; j0 += 16) {
@@ -506,7 +514,12 @@ k_fine(const float2* __restrict__ spec, int spec_stride, const int32_t* __restri
                 const int nslot = list ? list[nitem] : nitem;
                 fine_pass12(px, spec + (size_t)cycle_of[nslot] * spec_stride, 50 * cand_f0[nslot], tid - 128, TF, taper, tw);
             }
+            FP_T(tf2);
+            if (warp == 4) FP_ADD(14, tf2 - tf1);
         }
+        FP_T(tf3);
+        if (warp == 0) { FP_ADD(12, tf1 - tf0); FP_ADD(13, tf3 - tf1); }
+        if (warp == 3) { FP_ADD(15, tf3 - tf1); }
         __syncthreads();
     }
 }

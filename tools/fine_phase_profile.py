@@ -26,3 +26,9 @@ print("  consumer warp 0: window              : %.0f clk" % (v[4] / n))
 print("  consumer warp 0: window+bar+score    : %.0f clk" % (v[1] / n))
 print("  consumer warp 3: window+bar          : %.0f clk" % (v[5] / n))
 print("  producer warp 4: fused passes        : %.0f clk" % (v[2] / npd))
+nc = max(v[11], 1)
+print("per candidate (%d timed):" % nc)
+print("  time scan: pass (8,25)                 : %.0f clk" % (v[8] / nc))
+print("  time scan: consumer window+8 scores    : %.0f clk   producer fused passes: %.0f clk" % (v[9] / nc, v[10] / nc))
+print("  final: full last pass                  : %.0f clk" % (v[12] / nc))
+print("  final: warp 0 grid+llr %.0f clk, warp 3 grid %.0f clk, producer next-item passes %.0f clk" % (v[13] / nc, v[15] / nc, v[14] / nc))
