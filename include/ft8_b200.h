@@ -175,7 +175,8 @@ int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dtype, int B, 
  * batch on a second stream and returns at once.  A later ft8_decode_cycles(..., FT8_MEM_HOST) with the same pointer, dtype
  * and B consumes the prefetched copy instead of copying again, so the transfer of batch i+1 overlaps the kernels of batch
  * i.  The host buffer must stay valid and unchanged until that call; pinned memory is needed for the copy to be
- * asynchronous. */
+ * asynchronous.  Only the NEXT ft8_decode_cycles / ft8_decode_cycles_stream call can consume a prefetch: if that call
+ * names a different buffer, dtype or B, the pending prefetch is dropped (so a stale copy is never decoded later). */
 int ft8_prefetch_audio(ft8_handle* h, const void* audio_host, int audio_dtype, int B);
 
 /* Streaming form of ft8_decode_cycles for host audio: decodes `audio` (consuming its prefetched copy when there is one) and

@@ -849,7 +849,10 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
         CK(cudaStreamWaitEvent(h->stream, h->pf_ev, 0));
         da = h->d_audio;
         mem = FT8_MEM_DEVICE;
-    } else if (mem == FT8_MEM_HOST) { TRY(ensure_audio(h, (size_t)B * CYCLE_SAMPLES * esz)); da = h->d_audio; }
+    } else {
+        h->pf_host = nullptr;                    // a pending prefetch this call does not consume is dropped, never decoded later
+        if (mem == FT8_MEM_HOST) { TRY(ensure_audio(h, (size_t)B * CYCLE_SAMPLES * esz)); da = h->d_audio; }
+    }
     // streaming callers name the next batch: its copy is queued now and runs underneath this batch's kernels
     // (after this batch's own copies when it was not prefetched itself, so that they are not queued behind it)
     if (next_audio_host && prefetched) TRY(ft8_prefetch_audio(h, next_audio_host, audio_dtype, B));

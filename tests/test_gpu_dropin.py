@@ -141,3 +141,24 @@ def test_receiver_bank_decodes_golden_cycles_fed_hop_by_hop(golden_cycles):
     wf = bank.waterfall(0)
     assert wf.shape == (376, 976) and np.all(wf[0] == 1.0)
     bank.close()
+
+
+@pytest.mark.gpu
+def test_unconsumed_prefetch_is_dropped():
+    """A prefetch is consumed only by the very next decode call; otherwise it is dropped, so a later decode of the same
+    (meanwhile rewritten) host buffer sees the new samples, not the stale device copy."""
+    import torch
+    from pyft8_b200.engine import Engine
+    from pyft8_b200 import workload
+    eng = Engine(0, max_cycles=4)
+    prm = workload.make_params("cfg1_20sig", 8, seed=5)
+    a = torch.from_numpy(np.stack([workload.host_cycle(prm, i) for i in range(4)])).pin_memory().numpy()
+    b = np.stack([workload.host_cycle(prm, 4 + i) for i in range(4)])
+    want_a, want_b = eng.decode_cycles(a.copy()), eng.decode_cycles(b)
+    eng.prefetch(a)                        # pending copy of the OLD contents of `a`
+    eng.decode_cycles(b)                   # different buffer: the prefetch must be dropped here
+    a[:] = b                               # caller reuses the pinned buffer
+    got = eng.decode_cycles(a)
+    assert got[0].tobytes() == want_b[0].tobytes() and np.array_equal(got[1], want_b[1])
+    assert want_a[0].tobytes() != want_b[0].tobytes()
+    eng.close()
