@@ -201,7 +201,7 @@ class Engine:
                 raise ValueError("next_audio must have the dtype and shape of audio")
             self._pf_ref = nx
             self._check(self._lib.ft8_decode_cycles_stream(self._h, _ptr(a), dt, B, int(odd_even), _ptr(rec), cap, _ptr(n), _ptr(nx)))
-        return rec[:int(n.sum())], n
+        return rec[:int(n[:B].sum())], n[:B]
 
     def prefetch(self, audio):
         """Start copying the NEXT batch (host array, ideally pinned) while the current one is being decoded; the following
