@@ -219,7 +219,7 @@ class Engine:
             n = np.zeros(B, np.int32)
         self._check(self._lib.ft8_decode_cycles(self._h, C.c_void_p(audio_ptr), dtype, B, int(odd_even), _ptr(rec), len(rec),
                                                 _ptr(n), L.MEM_DEVICE))
-        return rec[:int(n.sum())], n
+        return rec[:int(n[:B].sum())], n[:B]
 
     def stats(self):
         s = L.Stats()
