@@ -252,7 +252,18 @@ def unpack_words(bits91_words):
     pos, keys = pos[order], keys[order]
     si = np.flatnonzero(seq)
     if len(si) == 0:
-        _register(keys)
+        # no history-dependent record in the batch: the end state only depends on the LAST registration of every distinct
+        # call, found in O(n) (fancy assignment keeps the last write) instead of sorting all registrations again
+        uid = np.concatenate([ia[ra], ib[rb]])[order]
+        if len(uid):
+            last = np.full(len(uk), -1, np.int64)
+            last[uid] = pos
+            live = np.flatnonzero(last >= 0)
+            for j in live[np.argsort(last[live], kind="stable")].tolist():
+                text, hs = _CALL_CACHE[int(uk[j])]
+                for h in hs:
+                    call_hashes[h] = text
+                hashes_for_calls[text] = list(hs)
         return out
     cuts = np.searchsorted(pos, 2 * si)
     b77 = fields_bits77(f, si)

@@ -285,30 +285,54 @@ def format_records(rec, cyclestart_strings=None):
     receiver.py:53-55.  Strings other than the message text are built only by MessageBatch.lines()/dicts()."""
     msgs = np.empty(len(rec), object)
     msgs[:] = unpack_words(rec["bits91"])
-    keep = np.array([m is not None for m in msgs.tolist()], bool)
-    text = np.array([" ".join(m) if m is not None else "" for m in msgs.tolist()], object)
     cyc = rec["cycle"].astype(np.int64)
-    if keep.any():                                      # first record of every (cycle, text) wins
+    valid = np.array([m is not None for m in msgs.tolist()], bool)
+    keep = np.zeros(len(rec), bool)
+    if valid.any():
+        # First record of every (cycle, text) wins (receiver.py:53-55).  Equal payloads give equal text, so de-duplicate on
+        # the packed payload first (cheap integer keys); different payloads can only render the same text through the
+        # hash table ('<...>' fields), so only those records are compared as strings afterwards.
+        vi = np.flatnonzero(valid)
+        w = np.asarray(rec["bits91"], np.uint32).reshape(-1, 3)[vi].astype(np.uint64)
+        k1 = (cyc[vi].astype(np.uint64) << np.uint64(32)) | w[:, 0]
+        k2 = (w[:, 1] << np.uint64(32)) | (w[:, 2] & np.uint64(0x1FFF))
+        order = np.lexsort((k2, k1))                       # stable: equal keys stay in record order
+        s1, s2 = k1[order], k2[order]
+        firsts = np.ones(len(vi), bool)
+        firsts[1:] = (s1[1:] != s1[:-1]) | (s2[1:] != s2[:-1])
+        keep[vi[order[firsts]]] = True
         ki = np.flatnonzero(keep)
-        _, inv = np.unique(text[ki].astype(str), return_inverse=True)
-        key = cyc[ki] * (int(inv.max()) + 1) + inv
-        _, first = np.unique(key, return_index=True)
-        keep[:] = False
-        keep[ki[first]] = True
+        hashed = np.array([("<" in m[0]) or ("<" in m[1]) for m in msgs[ki].tolist()], bool)
+        if hashed.any():
+            hi = ki[hashed]
+            texts = [" ".join(m) for m in msgs[hi].tolist()]
+            seen = set()
+            for i, c, t in zip(hi.tolist(), cyc[hi].tolist(), texts):
+                if (c, t) in seen:
+                    keep[i] = False
+                seen.add((c, t))
     fine = rec["ipass"] >= 2
     # python-float origin arithmetic of the reference (receiver.py:168-169, 350-351), in float64 like CPython
     tsec = rec["h0_idx"].astype(np.float64) / 25.0 + np.where(fine, rec["ttweak"].astype(np.float64) / 200, 0.0)
     fhz = 3.125 * rec["f0_idx"].astype(np.float64) + np.where(fine, rec["ftweak"].astype(np.float64) / 16, 0.0)
-    return MessageBatch(rec, msgs, text, keep, cyc, tsec, fhz, cyclestart_strings)
+    return MessageBatch(rec, msgs, keep, cyc, tsec, fhz, cyclestart_strings)
 
 
 class MessageBatch:
     """Columnar view of one decoded batch; rows flagged by .keep are what the reference would have emitted."""
 
-    def __init__(self, rec, msgs, text, keep, cycle, tsec, fhz, cyclestart_strings):
-        self.rec, self.msg_tuple, self.text, self.keep, self.cycle = rec, msgs, text, keep, cycle
+    def __init__(self, rec, msgs, keep, cycle, tsec, fhz, cyclestart_strings):
+        self.rec, self.msg_tuple, self.keep, self.cycle = rec, msgs, keep, cycle
+        self._text = None
         self.tsec, self.fHz, self.snr = tsec, fhz, rec["snr"].astype(np.int64)
         self.cyclestart_strings = cyclestart_strings
+
+    @property
+    def text(self):
+        """Message text per record (object array, '' for rejected payloads); built on first use."""
+        if self._text is None:
+            self._text = np.array([" ".join(m) if m is not None else "" for m in self.msg_tuple.tolist()], object)
+        return self._text
 
     def __len__(self):
         return int(self.keep.sum())
@@ -331,7 +355,7 @@ class MessageBatch:
         cs = self.cyclestart_strings
         css = [cs[c] for c in self.cycle[i].tolist()] if cs else [""] * len(i)
         return [f"{c} {s:+03d} {t - 0.6:4.1f} {f:4.0f} ~ {x}" for c, s, t, f, x in
-                zip(css, self.snr[i].tolist(), self.tsec[i].tolist(), self.fHz[i].tolist(), self.text[i].tolist())]
+                zip(css, self.snr[i].tolist(), self.tsec[i].tolist(), self.fHz[i].tolist(), [" ".join(m) for m in self.msg_tuple[i].tolist()])]
 
 
 class Receiver:
