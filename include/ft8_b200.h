@@ -172,11 +172,12 @@ int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dtype, int B, 
                       ft8_record* rec, int rec_capacity, int32_t* n_rec, int mem);
 
 /* Optional double buffering for callers that stream batches from host memory: starts the host->device copy of the NEXT
- * batch on a second stream and returns at once.  A later ft8_decode_cycles(..., FT8_MEM_HOST) with the same pointer, dtype
- * and B consumes the prefetched copy instead of copying again, so the transfer of batch i+1 overlaps the kernels of batch
- * i.  The host buffer must stay valid and unchanged until that call; pinned memory is needed for the copy to be
- * asynchronous.  Only the NEXT ft8_decode_cycles / ft8_decode_cycles_stream call can consume a prefetch: if that call
- * names a different buffer, dtype or B, the pending prefetch is dropped (so a stale copy is never decoded later). */
+ * batch on a second stream and returns at once.  The host buffer must stay valid and UNCHANGED until the copy has been
+ * consumed or dropped; pinned memory is needed for the copy to be asynchronous.  A pending prefetch is consumed only by
+ * the next ft8_decode_cycles_stream call whose `audio`, dtype and B are the ones that were prefetched -- by naming the
+ * buffer again through the streaming entry the caller states that it has not been rewritten.  Any other decode call
+ * (plain ft8_decode_cycles included, or a streaming call on a different buffer) waits for the pending copy to finish and
+ * drops it, so a stale device copy is never decoded and the host buffer is never read after that call returns. */
 int ft8_prefetch_audio(ft8_handle* h, const void* audio_host, int audio_dtype, int B);
 
 /* Streaming form of ft8_decode_cycles for host audio: decodes `audio` (consuming its prefetched copy when there is one) and

@@ -5,7 +5,9 @@ The reference runs one `Receiver` per audio device: a PyAudio callback appends 4
 deployment has hundreds of such streams; one B200 decodes ~30 k cycles/s, so the natural shape is: every stream appends
 into its own 15-s slot of a pinned [R, 180000] int16 batch, and when a cycle closes the whole batch goes through
 `ft8_decode_cycles_stream` once (isolated-cycle semantics) while the streams keep filling the other half of
-the double buffer.  Decoding runs on a worker thread, so `feed()` never blocks on the GPU.
+the double buffer.  Decoding runs on a worker thread; `feed()` only waits when it has to write into the half the decoder
+is still reading (a stream that runs a whole cycle ahead of the decoder).  `feed`/`feed_all` may be called from
+several audio threads: the ring positions and the close-of-cycle decision are guarded by one lock.
 
 What is kept from the reference surface: `on_message(dict)` with the keys of `check_and_package` (receiver.py:61-64)
 plus 'receiver'; `set_band(r, band)`; per-receiver waterfall rows on request (`waterfall(r)`, the 376 x 976 dB grid the
@@ -55,6 +57,7 @@ class ReceiverBank:
         self._results = queue.Queue()
         self._busy = set()                                # halves handed to the decoder and not yet released
         self._cv = threading.Condition()
+        self._state = threading.RLock()                   # guards _cyc/_pos/_open and the close-of-cycle decision
         self._eng_lock = threading.Lock()                 # one handle = one stream: calls are serialised
         self._worker = threading.Thread(target=self._run, daemon=True)
         self._worker.start()
@@ -77,6 +80,10 @@ class ReceiverBank:
         x = np.asarray(samples)
         if x.dtype != np.int16 or x.ndim != 1:
             raise TypeError("feed() takes a 1-D int16 block, as the reference's audio callback does")
+        with self._state:
+            return self._feed_locked(r, x)
+
+    def _feed_locked(self, r, x):
         closed = 0
         while len(x):
             c, p = int(self._cyc[r]), int(self._pos[r])
@@ -100,6 +107,10 @@ class ReceiverBank:
         b = np.asarray(block)
         if b.dtype != np.int16 or b.ndim != 2 or b.shape[0] != self.n:
             raise TypeError("feed_all() takes an int16 [n_receivers, k] block")
+        with self._state:
+            return self._feed_all_locked(b)
+
+    def _feed_all_locked(self, b):
         closed = 0
         while b.shape[1]:
             c, p = int(self._cyc[0]), int(self._pos[0])

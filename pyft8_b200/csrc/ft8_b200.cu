@@ -279,7 +279,7 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
             w96t.reserve((size_t)CS_N1 * CS_N2);
             for (int k1 = 0; k1 < CS_N1; ++k1)
                 for (int n2 = 0; n2 < CS_N2; ++n2) w96t.push_back(twiddle1(96000, (long long)n2 * k1));
-            if ((int)ts.size() != SP_T8_OFF + 7 * 16 || (int)tf.size() != FINE_TF_LEN || (int)tc.size() != 370) return fail(nullptr, FT8_E_CUDA, "twiddle table layout");
+            if ((int)ts.size() != SP_T8_OFF + 7 * 16 || (int)tf.size() != FINE_TF_LEN || (int)tc.size() != 370) { ft8_destroy(h); return fail(nullptr, FT8_E_CUDA, "twiddle table layout"); }
             CKC(upload(&h->d_TS, ts)); CKC(upload(&h->d_TF, tf)); CKC(upload(&h->d_TC, tc)); CKC(upload(&h->d_T256, t256));
             CKC(upload(&h->d_W96000T, w96t));
         }
@@ -303,7 +303,7 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
     CKC(dmalloc(&h->d_osd_found, N * 10)); CKC(dmalloc(&h->d_osd_bits, N * 30));
     CKC(dmalloc(&h->d_list_fine, N)); CKC(dmalloc(&h->d_list_osd, N)); CKC(dmalloc(&h->d_counts, 8));
     CKC(dmalloc(&h->d_stats, 1)); CKC(dmalloc(&h->d_rec, N)); CKC(dmalloc(&h->d_rec_n, B)); CKC(dmalloc(&h->d_rec_base, B));
-    CKC(cudaMallocHost((void**)&h->h_counts, 4 * sizeof(int32_t)));
+    CKC(cudaMallocHost((void**)&h->h_counts, 8 * sizeof(int32_t)));
     CKC(cudaMallocHost((void**)&h->h_stats, sizeof(DevStats)));
     {
         std::vector<int32_t> co(N);
@@ -417,6 +417,15 @@ static int launch_cycle_spectrum(ft8_handle* h, const void* d_audio, int dtype, 
 }
 
 static int persistent_blocks(ft8_handle* h, int per_sm) { return h->n_sm * per_sm; }
+
+// F2/F3 for a work list (list/count on the device) or for items 0..n_direct-1 (list == nullptr)
+static int launch_fine(ft8_handle* h, const float2* spec, int spec_stride, const int32_t* list, const int32_t* count, int n_direct,
+                       const int32_t* cycle_of, const int16_t* f0, const int16_t* h0, FineOut* fo, float* llr, float* sig_grid) {
+    const int blocks = list ? persistent_blocks(h, 4) : std::min(persistent_blocks(h, 4), n_direct);
+    k_fine<<<blocks, FINE_NT, FINE_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, fo, llr, sig_grid);
+    CK(cudaGetLastError());
+    return FT8_OK;
+}
 
 // copy helpers honouring the mem flag
 static int to_device(ft8_handle* h, void* d, const void* src, size_t bytes, int mem) {
@@ -562,43 +571,62 @@ extern "C" int ft8_cycle_spectrum(ft8_handle* h, const void* audio, int audio_dt
     return FT8_OK;
 }
 
+// ft8_fine helpers: range check of caller-supplied candidates on the device (works for host and device callers alike)
+// and the split of FineOut into the ABI's plain arrays.
+__global__ void k_fine_validate(const int32_t* __restrict__ cycle_of, const int16_t* __restrict__ f0, const int16_t* __restrict__ h0,
+                                int N, int B, int32_t* __restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && (h0[i] < -100 || h0[i] > 200 || f0[i] < 4 || f0[i] > 1880 || cycle_of[i] < 0 || cycle_of[i] >= B)) atomicAdd(bad, 1);
+}
+__global__ void k_fine_unpack(const FineOut* __restrict__ fo, int N, int32_t* __restrict__ tt, int32_t* __restrict__ ff,
+                              int32_t* __restrict__ ns, float* __restrict__ sd, int32_t* __restrict__ snr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) { const FineOut o = fo[i]; tt[i] = o.tt; ff[i] = o.ff; ns[i] = o.nsync; sd[i] = o.sd; snr[i] = o.snr; }
+}
+
 extern "C" int ft8_fine(ft8_handle* h, const float* spec, int B, const int32_t* cycle_of, const int16_t* f0_idx,
                         const int16_t* h0_idx, int N, int32_t* ttweak, int32_t* ftweak, int32_t* nsync, float* signal_grid,
                         float* llr, float* sd, int32_t* snr, int mem) {
     ENTER(h);
     if (!spec || !cycle_of || !f0_idx || !h0_idx || !ttweak || !ftweak || !nsync || !llr || !sd || !snr || N <= 0 || B <= 0)
         return fail(h, FT8_E_BADARG, "ft8_fine: bad argument");
-    if (mem == FT8_MEM_HOST)
-        for (int i = 0; i < N; ++i)
-            if (h0_idx[i] < -100 || h0_idx[i] > 200 || f0_idx[i] < 4 || f0_idx[i] > 1880 || cycle_of[i] < 0 || cycle_of[i] >= B)
-                return fail(h, FT8_E_BADARG, "ft8_fine: candidate outside the supported range (-100 <= h0 <= 200, 4 <= f0 <= 1880)");
     const size_t specn = (size_t)B * FT8_SPEC_BINS;
-    size_t need = specn * 8 + (size_t)N * (4 + 2 + 2 + sizeof(FineOut) + 174 * 4 + 632 * 4) + 8 * 256;
+    size_t need = specn * 8 + (size_t)N * (4 + 2 + 2 + sizeof(FineOut) + 174 * 4 + 632 * 4 + 5 * 4) + 16 * 256;
     TRY(ensure_arena(h, need));
     Carver c{(char*)h->arena};
     float2* dspec = c.take<float2>(specn);
     int32_t* dco = c.take<int32_t>(N); int16_t* df0 = c.take<int16_t>(N); int16_t* dh0 = c.take<int16_t>(N);
     FineOut* dfo = c.take<FineOut>(N); float* dllr = c.take<float>((size_t)N * 174); float* dsg = c.take<float>((size_t)N * 632);
+    int32_t* dtt = c.take<int32_t>(N); int32_t* dff = c.take<int32_t>(N); int32_t* dns = c.take<int32_t>(N);
+    float* dsd = c.take<float>(N); int32_t* dsn = c.take<int32_t>(N); int32_t* dbad = c.take<int32_t>(1);
     const float2* sp = (const float2*)spec;
     if (mem == FT8_MEM_HOST) { TRY(to_device(h, dspec, spec, specn * 8, mem)); sp = dspec; }
     TRY(to_device(h, dco, cycle_of, (size_t)N * 4, mem));
     TRY(to_device(h, df0, f0_idx, (size_t)N * 2, mem));
     TRY(to_device(h, dh0, h0_idx, (size_t)N * 2, mem));
-    k_fine<<<std::min(persistent_blocks(h, 4), N), FINE_NT, FINE_SMEM_BYTES, h->stream>>>(
-        sp, FT8_SPEC_BINS, nullptr, nullptr, N, dco, df0, dh0, h->d_TF, dfo, dllr, signal_grid ? dsg : nullptr);
+    // candidates are range-checked on the device before anything gathers with them (host AND device callers)
+    CK(cudaMemsetAsync(dbad, 0, 4, h->stream));
+    k_fine_validate<<<(N + 255) / 256, 256, 0, h->stream>>>(dco, df0, dh0, N, B, dbad);
     CK(cudaGetLastError());
-    std::vector<FineOut> fo(N);
-    CK(cudaMemcpyAsync(fo.data(), dfo, (size_t)N * sizeof(FineOut), cudaMemcpyDeviceToHost, h->stream));
-    TRY(from_device(h, llr, dllr, (size_t)N * 174 * 4, mem));
-    if (signal_grid) TRY(from_device(h, signal_grid, dsg, (size_t)N * 632 * 4, mem));
+    CK(cudaMemcpyAsync(h->h_counts + 3, dbad, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    std::vector<int32_t> t(N), f(N), ns(N), sn(N);
-    std::vector<float> s(N);
-    for (int i = 0; i < N; ++i) { t[i] = fo[i].tt; f[i] = fo[i].ff; ns[i] = fo[i].nsync; s[i] = fo[i].sd; sn[i] = fo[i].snr; }
-    const cudaMemcpyKind kind = mem == FT8_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice;
-    CK(cudaMemcpy(ttweak, t.data(), (size_t)N * 4, kind)); CK(cudaMemcpy(ftweak, f.data(), (size_t)N * 4, kind));
-    CK(cudaMemcpy(nsync, ns.data(), (size_t)N * 4, kind)); CK(cudaMemcpy(sd, s.data(), (size_t)N * 4, kind));
-    CK(cudaMemcpy(snr, sn.data(), (size_t)N * 4, kind));
+    if (h->h_counts[3] != 0)
+        return fail(h, FT8_E_BADARG, "ft8_fine: candidate outside the supported range (-100 <= h0 <= 200, 4 <= f0 <= 1880, 0 <= cycle_of < B)");
+    float* out_llr = mem == FT8_MEM_HOST ? dllr : llr;
+    float* out_sg = signal_grid ? (mem == FT8_MEM_HOST ? dsg : signal_grid) : nullptr;
+    TRY(launch_fine(h, sp, FT8_SPEC_BINS, nullptr, nullptr, N, dco, df0, dh0, dfo, out_llr, out_sg));
+    const bool host = mem == FT8_MEM_HOST;
+    k_fine_unpack<<<(N + 255) / 256, 256, 0, h->stream>>>(dfo, N, host ? dtt : ttweak, host ? dff : ftweak, host ? dns : nsync,
+                                                          host ? dsd : sd, host ? dsn : snr);
+    CK(cudaGetLastError());
+    if (host) {
+        TRY(from_device(h, ttweak, dtt, (size_t)N * 4, mem)); TRY(from_device(h, ftweak, dff, (size_t)N * 4, mem));
+        TRY(from_device(h, nsync, dns, (size_t)N * 4, mem)); TRY(from_device(h, sd, dsd, (size_t)N * 4, mem));
+        TRY(from_device(h, snr, dsn, (size_t)N * 4, mem));
+        TRY(from_device(h, llr, dllr, (size_t)N * 174 * 4, mem));
+        if (signal_grid) TRY(from_device(h, signal_grid, dsg, (size_t)N * 632 * 4, mem));
+    }
+    CK(cudaStreamSynchronize(h->stream));
     return FT8_OK;
 }
 
@@ -827,7 +855,7 @@ extern "C" int ft8_prefetch_audio(ft8_handle* h, const void* audio_host, int aud
 }
 
 static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even, ft8_record* rec,
-                              int rec_capacity, int32_t* n_rec, int mem, const void* next_audio_host) {
+                              int rec_capacity, int32_t* n_rec, int mem, const void* next_audio_host, bool consume_pf) {
     ENTER(h);
     if (!audio || !rec || !n_rec || B <= 0 || rec_capacity < 0) return fail(h, FT8_E_BADARG, "ft8_decode_cycles: bad argument");
     if ((size_t)B > h->cap_cycles) return fail(h, FT8_E_CAPACITY, "ft8_decode_cycles: B exceeds cfg.max_cycles");
@@ -839,7 +867,11 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
     if (audio_dtype != FT8_AUDIO_I16 && audio_dtype != FT8_AUDIO_F32) return fail(h, FT8_E_BADARG, "audio_dtype must be FT8_AUDIO_I16 or FT8_AUDIO_F32");
     const size_t esz = audio_dtype == FT8_AUDIO_I16 ? 2 : 4;
     const void* da = audio;
-    const bool prefetched = mem == FT8_MEM_HOST && h->pf_host == audio && h->pf_B == B && h->pf_dtype == audio_dtype;
+    // A pending prefetch is consumed only by the streaming entry (consume_pf), whose caller named this very buffer as the
+    // next batch and so promises it has not been rewritten since; every other call drops it -- after waiting for its copy,
+    // which may still be reading the caller's host buffer.
+    const bool prefetched = consume_pf && mem == FT8_MEM_HOST && h->pf_host == audio && h->pf_B == B && h->pf_dtype == audio_dtype;
+    if (!prefetched && h->pf_host) CK(cudaStreamSynchronize(h->copy_stream));
     if (prefetched) {
         // this batch was copied by ft8_prefetch_audio while the previous call was computing: swap it in and go on as if
         // the audio were device-resident
@@ -911,10 +943,9 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
     CK(cudaGetLastError()); ++launches;
     CK(cudaEventRecord(h->ev[4], h->stream));
     // ipass 1
-    k_fine<<<persistent_blocks(h, 4), FINE_NT, FINE_SMEM_BYTES, h->stream>>>(
-        h->d_spec, FINE_SPEC_STRIDE, h->d_list_fine, h->d_counts + 0, 0, h->d_cycle_of, h->d_f0, h->d_h0, h->d_TF, h->d_fine,
-        h->d_llr_fine, nullptr);
-    CK(cudaGetLastError()); ++launches;
+    TRY(launch_fine(h, h->d_spec, FINE_SPEC_STRIDE, h->d_list_fine, h->d_counts + 0, 0, h->d_cycle_of, h->d_f0, h->d_h0, h->d_fine,
+                    h->d_llr_fine, nullptr));
+    ++launches;
     CK(cudaEventRecord(h->ev[5], h->stream));
     // ipass 2-4
     k_pass234<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
@@ -965,12 +996,12 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
 
 extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even, ft8_record* rec,
                                  int rec_capacity, int32_t* n_rec, int mem) {
-    return decode_cycles_core(h, audio, audio_dtype, B, odd_even, rec, rec_capacity, n_rec, mem, nullptr);
+    return decode_cycles_core(h, audio, audio_dtype, B, odd_even, rec, rec_capacity, n_rec, mem, nullptr, false);
 }
 
 extern "C" int ft8_decode_cycles_stream(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even, ft8_record* rec,
                                         int rec_capacity, int32_t* n_rec, const void* next_audio_host) {
-    return decode_cycles_core(h, audio, audio_dtype, B, odd_even, rec, rec_capacity, n_rec, FT8_MEM_HOST, next_audio_host);
+    return decode_cycles_core(h, audio, audio_dtype, B, odd_even, rec, rec_capacity, n_rec, FT8_MEM_HOST, next_audio_host, true);
 }
 
 // ------------------------------------------------------------------------------------------ generator + test hook

@@ -5,6 +5,7 @@ device pointers (e.g. ``torch.Tensor.data_ptr()``), PyTorch being only an option
 RuntimeError(ft8_last_error()).  Reference call sites replaced by each method are cited in include/ft8_b200.h.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -31,10 +32,38 @@ def int_to_bits91(v):
     return np.array(w, np.uint32)
 
 
+class _SerialisedLib:
+    """Per-handle call gate.  One ft8_handle = one stream + one scratch arena, so its entry points must not run
+    concurrently -- but ctypes releases the GIL, and the live Receiver calls the same handle
+    from the audio callback (`hop_spectrum`) and from `manage_cycle` (`ft8_llr/ldpc/osd/fine`).  Every library call of
+    an Engine therefore goes through this proxy, which holds the engine's lock for the duration of the call and, on
+    failure, reads ft8_last_error while still holding it (kept per thread for `_check`)."""
+
+    def __init__(self, lib, lock):
+        self._lib, self._lock, self._tls = lib, lock, threading.local()
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        takes_handle = name not in ("ft8_default_cfg", "ft8_create")
+
+        def call(*args):
+            with self._lock:
+                rc = fn(*args)
+                if takes_handle and fn.restype is C.c_int and rc != L.OK:
+                    self._tls.err = self._lib.ft8_last_error(args[0]).decode()
+                return rc
+        setattr(self, name, call)
+        return call
+
+    def last_error(self):
+        return getattr(self._tls, "err", "")
+
+
 class Engine:
     def __init__(self, device=0, max_cycles=1, max_cands=200, sync_score_min=85.0, llr_sd_min=5.0,
                  osd_singleflips=30, osd_doubleflips=2):
-        self._lib = L.load()
+        self._lock = threading.RLock()
+        self._lib = _SerialisedLib(L.load(), self._lock)
         cfg = L.Cfg()
         self._lib.ft8_default_cfg(C.byref(cfg))
         cfg.max_cycles, cfg.max_cands = int(max_cycles), int(max_cands)
@@ -63,7 +92,7 @@ class Engine:
 
     def _check(self, rc):
         if rc != L.OK:
-            raise RuntimeError(f"libft8_b200 error {rc}: {self._lib.ft8_last_error(self._h).decode()}")
+            raise RuntimeError(f"libft8_b200 error {rc}: {self._lib.last_error()}")
 
     @staticmethod
     def _audio(audio):
@@ -193,14 +222,20 @@ class Engine:
         elif n.dtype != np.int32 or len(n) < B or not n.flags.c_contiguous:
             raise ValueError("n must be a contiguous int32 array of at least B entries")
         cap = len(rec)
-        if next_audio is None:
+        pending = getattr(self, "_pf_ref", None)
+        # a prefetched copy is consumed only through the streaming entry, and only for the very array that was named
+        mine = pending is not None and pending.ctypes.data == a.ctypes.data and pending.shape == a.shape
+        if next_audio is None and not mine:
             self._check(self._lib.ft8_decode_cycles(self._h, _ptr(a), dt, B, int(odd_even), _ptr(rec), cap, _ptr(n), L.MEM_HOST))
+            self._pf_ref = None                            # the library waited for (and dropped) any pending copy
         else:
-            nx, ndt = self._audio(next_audio)
-            if ndt != dt or nx.shape != a.shape:
-                raise ValueError("next_audio must have the dtype and shape of audio")
-            self._pf_ref = nx
+            nx = None
+            if next_audio is not None:
+                nx, ndt = self._audio(next_audio)
+                if ndt != dt or nx.shape != a.shape:
+                    raise ValueError("next_audio must have the dtype and shape of audio")
             self._check(self._lib.ft8_decode_cycles_stream(self._h, _ptr(a), dt, B, int(odd_even), _ptr(rec), cap, _ptr(n), _ptr(nx)))
+            self._pf_ref = nx                              # keeps the host buffer alive until its copy is consumed or dropped
         return rec[:int(n[:B].sum())], n[:B]
 
     def prefetch(self, audio):

@@ -119,6 +119,7 @@ def unpack(bits):
 # ('<...>' fields, type-4 messages) go through the scalar unpack(), at their position in the sequence.
 import numpy as np
 
+_CALL_CACHE_MAX = 1 << 21
 _CALL_CACHE = {}          # c29 * 2 + (i3 == 2) -> (text | None, (h10, h12, h22) | None when nothing is registered)
 _EXTRA = None             # g16 -> text ("" and None = reject; None also means: calls are not even evaluated)
 _EXTRA_EVAL = _EXTRA_OK = None
@@ -193,14 +194,15 @@ def fields_bits77(f, idx=None):
     return [(int(h) << 13) | int(t) for h, t in zip(hi.tolist(), tail.tolist())]
 
 
-def _register(keys_in_order):
-    """Apply add_call_hashes for a sequence of cached call keys with the end state of doing it one by one."""
+def _register(keys_in_order, ents):
+    """Apply add_call_hashes for a sequence of call keys with the end state of doing it one by one.
+    `ents` is the batch-local {key: (text, hashes)} map (never the global cache, which may be evicted between batches)."""
     if not len(keys_in_order):
         return
     rev = keys_in_order[::-1]
     uk, first_rev = np.unique(rev, return_index=True)          # first in reversed order = last occurrence
     for k in uk[np.argsort(-first_rev, kind="stable")].tolist():   # ascending last occurrence
-        text, hs = _CALL_CACHE[k]
+        text, hs = ents[k]
         for h in hs:
             call_hashes[h] = text
         hashes_for_calls[text] = list(hs)
@@ -229,12 +231,16 @@ def unpack_words(bits91_words):
     utext = np.empty(len(uk), object)
     ureg = np.zeros(len(uk), bool)
     uok = np.zeros(len(uk), bool)
+    # the global cache is only evicted BETWEEN batches; everything this batch needs later (registration replay) is read
+    # from the batch-local map `ents`, so an eviction can never pull an entry out from under a batch
+    if len(_CALL_CACHE) > _CALL_CACHE_MAX:
+        _CALL_CACHE.clear()
+    ents = {}
     for j, k in enumerate(uk.tolist()):
         ent = _CALL_CACHE.get(k)
         if ent is None:
-            if len(_CALL_CACHE) > 1 << 21:
-                _CALL_CACHE.clear()
             ent = _CALL_CACHE[k] = _call29_pure(k >> 1, k & 1)
+        ents[k] = ent
         utext[j], ureg[j], uok[j] = ent[0], ent[1] is not None, ent[0] is not None
     ia, ib = inv[:len(vi)], inv[len(vi):]
     rega, regb = ureg[ia], ureg[ib]
@@ -260,7 +266,7 @@ def unpack_words(bits91_words):
             last[uid] = pos
             live = np.flatnonzero(last >= 0)
             for j in live[np.argsort(last[live], kind="stable")].tolist():
-                text, hs = _CALL_CACHE[int(uk[j])]
+                text, hs = ents[int(uk[j])]
                 for h in hs:
                     call_hashes[h] = text
                 hashes_for_calls[text] = list(hs)
@@ -269,10 +275,10 @@ def unpack_words(bits91_words):
     b77 = fields_bits77(f, si)
     lo = 0
     for c, i, b in zip(cuts.tolist(), si.tolist(), b77):
-        _register(keys[lo:c])
+        _register(keys[lo:c], ents)
         lo = c
         out[i] = unpack(b)
-    _register(keys[lo:])
+    _register(keys[lo:], ents)
     return out
 
 

@@ -40,7 +40,13 @@ ap_patterns = [
 
 
 class Candidate:
-    """One sync candidate and its pass state machine (receiver.py:29-222), each step executed by the CUDA library."""
+    """One sync candidate and its pass state machine, each step executed by the CUDA library.
+
+    INTERFACE MIRROR, not a built component: attribute names, the pass table of `decode`, `_set_AP` and the dict of
+    `check_and_package` follow reference receiver.py:29-134 statement by statement on purpose, so that code written
+    against the reference's Candidate keeps working; it carries no DSP (that is csrc/passes.cuh, which the batched
+    path uses instead of this class).  Where the reference itself is installed, INTEGRATION.md section 2's import
+    swap makes this class unnecessary."""
 
     def __init__(self, origin, search_grid_bounds, payload_on_search_grid, get_cycle_spectrum, on_message, llr_sd_min=5,
                  engine=None, time_utils=None):

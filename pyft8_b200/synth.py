@@ -6,8 +6,8 @@ computes -- 77-bit packing of standard messages (transmitter.py:97-174), CRC-14 
 (transmitter.py:208-223), parity bits from the generator rows (transmitter.py:181-187), Gray map
 and Costas framing (transmitter.py:189-206) and the BT=2.0 Gaussian-smoothed phase modulator
 (transmitter.py:41-70) -- so that the GPU box, where the reference tree is absent, can build the
-same signals.  ``tests/test_synth_golden.py`` pins it against vectors made with the unmodified
-reference.  The mixing recipe (amplitude convention, seeds) is SURVEY.md section 8d.
+same signals.  ``tests/test_oracle_golden.py`` (encoder / CRC / modulator known answers) pins it against vectors
+made with the unmodified reference.  The mixing recipe (amplitude convention, seeds) is SURVEY.md section 8d.
 """
 import math
 

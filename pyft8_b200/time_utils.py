@@ -5,16 +5,25 @@ import time as _time
 
 
 class TimeUtils:
-    def __init__(self, clock=None):
+    def __init__(self, clock=None, sleep_fn=None):
         self.cycle_seconds = 15
         self._clock = clock or _time.time
+        self._sleep_fn = sleep_fn
 
     def time(self):
         return self._clock()
 
     def sleep(self, t):
-        if self._clock is _time.time and t > 0:
+        """Real clock: sleep t.  Injected clock: call sleep_fn(t) if one was given, else yield the CPU for at most 10 ms
+        of real time (a polling loop on a fake clock must neither spin nor stall the test that advances the clock)."""
+        if t <= 0:
+            return
+        if self._sleep_fn is not None:
+            self._sleep_fn(t)
+        elif self._clock is _time.time:
             _time.sleep(t)
+        else:
+            _time.sleep(min(t, 0.01))
 
     def set_cycle_length(self, dur):
         self.cycle_seconds = dur

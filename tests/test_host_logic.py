@@ -138,6 +138,20 @@ def test_unpack_many_equals_sequential_unpack_with_hash_history():
     assert messages.unpack_many(seq) == want
 
 
+def test_unpack_many_survives_call_cache_eviction(monkeypatch):
+    """the call cache used to be cleared in the middle of a batch, then read back -> KeyError."""
+    rng = np.random.default_rng(5)
+    seq = [synth.pack77(*synth.random_message(rng)) for _ in range(50)]
+    messages.call_hashes.clear()
+    messages._CALL_CACHE.clear()
+    want = [messages.unpack(b) for b in seq]
+    monkeypatch.setattr(messages, "_CALL_CACHE_MAX", 8)          # every batch starts by evicting the previous one
+    for _ in range(3):
+        messages.call_hashes.clear()
+        assert messages.unpack_many(seq) == want
+        assert len(messages.call_hashes) > 0                      # registrations were replayed from the batch-local map
+
+
 def test_records_bits77_vectorised():
     from pyft8_b200.receiver import records_bits77
     rng = np.random.default_rng(4)
