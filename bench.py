@@ -2,18 +2,27 @@
 """bench.py -- decoded 15-s FT8 cycles/s of the receive hot path on B200 (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU under torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm (oracle port) on the host cores
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU implementation on the host cores
 
 A step = one pass of the whole path (audio -> records) over one batch of synthetic cycles (BASELINE configs[1]:
 4096 cycles x 50 GFSK signals, SNR -24..+10 dB, 200-2950 Hz).  `value` is timed with the batch resident in HBM;
 `e2e` is the same through Engine.decode_cycles with pinned HOST buffers (H2D of the audio and D2H of the records inside
-the timed region).  Prints ONE JSON line on rank 0.
+the timed region; at N > 1 the host-side gather of every rank's records on rank 0 as well).  Prints ONE JSON line on
+rank 0.  The default N = 1 run also measures BASELINE configs[2] (LDPC/OSD codewords/s) and configs[3] (dense band) in
+the same process, outside the headline timed region (`configs`).
+
+Roofline block: nothing is typed in here.  Algorithmic bytes are SURVEY 8d's (ALG_BYTES below, derivation in DESIGN.md
+section 4); the ncu-derived quantities (DRAM traffic, pipe utilisation per kernel) are loaded from
+profiles/ncu_current.json (tools/ncu_extract.py output, tagged with the commit it was captured at and printed as
+`ncu_capture_commit`); on-chip peaks come from profiles/peaks_b200.json (tools/micro/peaks.cu run on the box) and the HBM
+peak from MEASURED_PEAKS.json.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -25,7 +34,8 @@ import numpy as np  # noqa: E402
 METRIC = "decoded 15-s FT8 cycles/sec"
 UNIT = "cycles/s"
 WORKLOAD = "cfg2_50sig"          # BASELINE configs[1]; --workload selects configs[0] / configs[3] shapes for extra data points
-# algorithmic bytes per unit (DESIGN.md "Roofline accounting"); int16 audio in
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")     # unmodified reference, pip-installed by __graft_entry__.build()
+# algorithmic bytes per unit; int16 audio in
 ALG_BYTES = {
     "spectrogram": 360000 + 375 * 976 * 4,          # per cycle: audio once + grid once
     "sync": 375 * 976 * 4 + 200 * (16 + 58 * 8 * 4),  # per cycle: grid once + candidates/payloads
@@ -35,28 +45,97 @@ ALG_BYTES = {
     "pass234_ldpc": 696 + 696 + 24,                 # per LDPC call
     "osd": 696 + 64,                                # per OSD call
 }
-# measured DRAM traffic per cycle (bytes) of each stage's kernels: dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture at 4096 cycles/launch, divided by 4096 (profiles/r01i_summary.md; osd from the earlier r01e capture, its kernel is unchanged)
-NCU_DRAM_BYTES_PER_CYCLE = {"spectrogram": (1477e6 + 5959e6) / 4096, "sync": (2328e6 + 49e6 + 46e6) / 4096, "fine": (2892e6 + 492e6) / 4096,
-                            "pass0_ldpc5": (3733e6 + 616e6) / 4096, "osd": (541e6 + 25e6) / 4096,
-                            "cycle_spectrum": (787e6 + 370e6 + 369e6 + 732e6) / 1024}
-# issue-slot / pipe utilisation of the same captures (percent of peak): what actually bounds the non-HBM stages.
-# l1_data_pipe = l1tex__data_pipe_lsu_wavefronts (shared-memory + L1 wavefronts): the binding resource of the FFT kernels.
-NCU_PIPES = {"spectrogram": {"issue_active": 72.3, "fma_pipe": 31.7, "alu_pipe": 37.7, "l1_data_pipe": 86.4},
-             "sync": {"issue_active": 75.2, "fma_pipe": 25.9, "alu_pipe": 43.4, "l1_data_pipe": 85.9},
-             "cycle_spectrum": {"issue_active": 45.1, "fma_pipe": 16.4, "alu_pipe": 30.7, "l1_data_pipe": 88.3},
-             "fine": {"issue_active": 48.0, "fma_pipe": 22.9, "alu_pipe": 19.8, "l1_data_pipe": 64.0},
-             "pass0_ldpc5": {"issue_active": 56.7, "fma_pipe": 21.4, "alu_pipe": 24.0, "l1_data_pipe": 71.1},
-             "osd": {"issue_active": 67.2, "fma_pipe": 6.5, "alu_pipe": 84.1}}
 STAGES = ["all", "spectrogram", "sync", "cycle_spectrum", "pass0_ldpc5", "fine", "pass234_ldpc", "osd", "collect"]
+# kernels of each stage (names as tools/ncu_extract.py shortens them) and the work unit its per-unit figures refer to
+STAGE_KERNELS = {"spectrogram": ["k_spectrogram"], "sync": ["k_sync_scores", "k_topk"], "cycle_spectrum": ["k_cs_cols", "k_cs_rows"],
+                 "pass0_ldpc5": ["k_pass0"], "fine": ["k_fine", "k_fine_tscan", "k_fscan_mma", "k_fine_final"],
+                 "pass234_ldpc": ["k_pass234"], "osd": ["k_osd_items", "k_osd_resolve"]}
+STAGE_UNIT = {"spectrogram": "cycles", "sync": "cycles", "cycle_spectrum": "cycles", "pass0_ldpc5": "candidates", "fine": "fine_evals",
+              "pass234_ldpc": "ldpc_calls", "osd": "osd_calls"}
+# what bounds a stage when the committed capture has no counters for its kernels (stated, frac left null -- never "hbm")
+DECLARED_BOUND = {"pass0_ldpc5": "fp32", "fine": "l1_data_pipe", "pass234_ldpc": "fp32", "osd": "int_alu"}
+HBM_STAGES = ("spectrogram", "sync", "cycle_spectrum")          # the stages the north star holds against the HBM roofline
+# on-chip roofs: name -> (ncu utilisation key in the capture, peak key in profiles/peaks_b200.json, unit)
+ONCHIP = {"l1_data_pipe": ("l1_data_pipe_pct", "l1_wavefronts_per_s_lds64", "wavefronts/s"),
+          "fp32": ("fma_pipe_pct", "fma_warp_inst_per_s", "warp-inst/s"),
+          "int_alu": ("alu_pipe_pct", "int_alu_warp_inst_per_s", "warp-inst/s"),
+          "tensor": ("tensor_pipe_pct", "tf32_dense_tflops", "TFLOP/s")}
+
+
+def _load_json(path):
+    try:
+        return json.load(open(path))
+    except Exception:
+        return None
 
 
 def _peaks():
-    try:
-        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    p = _load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
+    if p and "hbm_gbs" in p:
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def roofline_block(stage_ms, units, cycles):
+    """Per-stage roofline entries from live CUDA-event times + the committed capture / peak files (see module docstring)."""
+    hbm_peak, hbm_src = _peaks()
+    cap = _load_json(os.path.join(ROOT, "profiles", "ncu_current.json")) or {}
+    onchip_peaks = _load_json(os.path.join(ROOT, "profiles", "peaks_b200.json")) or {}
+    kern = cap.get("kernels", {})
+    cap_units = dict(cap.get("work_per_step") or {})
+    cap_units["cycles"] = cap.get("cycles_per_launch")
+    stages = []
+    for i, name in enumerate(STAGES):
+        if name not in ALG_BYTES:
+            continue
+        ms = float(stage_ms[i])
+        n_units = units[STAGE_UNIT[name]]
+        ent = {"kernel": name, "ms": round(ms, 4), "share": round(ms / float(stage_ms[0]), 4) if stage_ms[0] > 0 else None,
+               "unit_of_work": STAGE_UNIT[name], "units": int(n_units)}
+        ks = [k for k in STAGE_KERNELS[name] if k in kern]
+        # per-step totals of the captured kernels of this stage (average launch x launches per step)
+        t_cap = sum(kern[k]["time_ms"] * kern[k].get("launches_per_step", 1) for k in ks)
+        cu = cap_units.get(STAGE_UNIT[name])
+        scale = (n_units / cu) if (cu and ks) else None            # live units / captured units
+        traffic = int(sum(kern[k]["dram_bytes"] * kern[k].get("launches_per_step", 1) for k in ks) * scale) if scale else None
+        util = {}
+        for roof, (key, _, _) in ONCHIP.items():
+            if ks and t_cap > 0 and all(key in kern[k] for k in ks):
+                util[roof] = sum(kern[k][key] * kern[k]["time_ms"] * kern[k].get("launches_per_step", 1) for k in ks) / t_cap
+        # the same pipe work per unit in the live time: utilisation scales with captured time per unit / live time per unit
+        live = {r: u * (t_cap * scale / ms) for r, u in util.items()} if (scale and ms > 0) else {}
+        alg = ALG_BYTES[name] * n_units
+        hbm_ach = alg / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        onchip_best = max(live, key=live.get) if live else None
+        if name not in HBM_STAGES and onchip_best is None:
+            ent.update({"bound": DECLARED_BOUND[name], "achieved": None, "peak": None, "unit": ONCHIP[DECLARED_BOUND[name]][2], "frac": None,
+                        "note": "no ncu counters for this stage in the committed capture"})
+        elif name in HBM_STAGES:
+            ent.update({"bound": "hbm", "achieved": round(hbm_ach, 2), "peak": hbm_peak, "unit": "GB/s", "frac": round(hbm_ach / hbm_peak, 5)})
+        else:
+            _, pkey, punit = ONCHIP[onchip_best]
+            peak = onchip_peaks.get(pkey)
+            frac = live[onchip_best] / 100.0
+            ent.update({"bound": onchip_best, "achieved": (frac * peak) if peak else None, "peak": peak, "unit": punit, "frac": round(frac, 5)})
+        if onchip_best is not None:
+            _, pkey, punit = ONCHIP[onchip_best]
+            ent["on_chip"] = {"bound": onchip_best, "frac": round(live[onchip_best] / 100.0, 5), "peak": onchip_peaks.get(pkey), "unit": punit}
+        ent["hbm_frac"] = round(hbm_ach / hbm_peak, 5)
+        ent["alg_bytes"] = int(alg)
+        ent["traffic"] = traffic
+        ent["ncu_pct_of_peak_at_capture"] = {k: round(v, 1) for k, v in util.items()} or None
+        stages.append(ent)
+    dom = max(stages, key=lambda s: s["ms"])
+    roofline = {k: dom.get(k) for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic")}
+    roofline.update({"hbm_peak_source": hbm_src, "ncu_capture": cap.get("capture"), "ncu_capture_commit": cap.get("commit"),
+                     "onchip_peaks": "profiles/peaks_b200.json" if onchip_peaks else None,
+                     "note": "dominant kernel by device time; per stage: bound = hbm for S1/S2/F1 (north star) with the on-chip roof "
+                             "beside it, else the most utilised on-chip pipe of the committed ncu capture rescaled to the live time"})
+    s12 = [s for s in stages if s["kernel"] in ("spectrogram", "sync")]
+    s12_ms = sum(s["ms"] for s in s12)
+    roofline["s1_s2"] = {"ms": round(s12_ms, 4), "alg_bytes": int(sum(s["alg_bytes"] for s in s12)),
+                         "hbm_frac": round(sum(s["alg_bytes"] for s in s12) / (s12_ms / 1e3) / 1e9 / hbm_peak, 5) if s12_ms > 0 else None}
+    return roofline, stages
 
 
 class ClockSampler:
@@ -103,18 +182,33 @@ def _dist_init():
     if world > 1:
         import torch.distributed as dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # no data-path collective exists (cycles are independent); gloo carries the barrier and the max-over-ranks
+        # no data-path collective exists (cycles are independent); gloo carries the barrier, the max-over-ranks and the
+        # host-side record gather
         dist_mod.init_process_group("gloo", rank=rank, world_size=world)
         dist = dist_mod
     return dist, rank, local, world
 
 
+# ---------------------------------------------------------------------------------------------- CPU arms
+def ref_available():
+    return os.path.isdir(os.path.join(REF_DIR, "PyFT8"))
+
+
 def _cpu_decode_one(a):
+    """One cycle on one host core: the UNMODIFIED reference (oracle/_ref, driven through its own Receiver / AudioIn /
+    Candidate API by oracle/ref_harness.py) when it travelled to this box, else the numpy port (oracle/ft8_oracle.py).
+    Returns (texts of the emitted messages, n candidates, n ldpc calls | None, seconds)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import ft8_oracle as o
     t = time.time()
+    if ref_available():
+        os.environ["PYFT8_REF_ROOT"] = REF_DIR
+        import ref_harness as rh
+        with tempfile.TemporaryDirectory() as d:
+            out = rh.decode_cycle(a, workdir=d)
+        return [" ".join(m["msg_tuple"]) for m in out["messages"]], out["n_cands"], None, time.time() - t
+    import ft8_oracle as o
     recs, cl = o.decode_cycle(a)
-    return len(recs), len(cl), sum(c.n_ldpc for c in cl), sum(c.n_osd for c in cl), time.time() - t
+    return [" ".join(o.unpack77(r["bits77"]) or ()) for r in recs], len(cl), sum(c.n_ldpc for c in cl), time.time() - t
 
 
 _POOL = None
@@ -122,12 +216,17 @@ _POOL = None
 
 def _cpu_warm(_):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import ft8_oracle  # noqa: F401
+    if ref_available():
+        os.environ["PYFT8_REF_ROOT"] = REF_DIR
+        import ref_harness as rh
+        rh.load_reference()
+    else:
+        import ft8_oracle  # noqa: F401
     return os.getpid()
 
 
 def cpu_pool(cores):
-    """Worker processes (one per host core) with the oracle imported, so that timing excludes process start-up."""
+    """Worker processes (one per host core) with the CPU implementation imported, so that timing excludes start-up."""
     global _POOL
     if _POOL is None:
         import multiprocessing as mp
@@ -145,18 +244,24 @@ def _host_cycle0(p):
 
 
 def cpu_rate(cycles, cores):
-    """The oracle port on `cores` worker processes, one cycle at a time each: (cycles/s, ldpc calls/s, detail)."""
+    """The CPU implementation on `cores` worker processes, one cycle at a time each: (cycles/s, ldpc calls/s | None, detail)."""
     pool = cpu_pool(cores)
     t = time.time()
     res = pool.map(_cpu_decode_one, list(cycles), chunksize=1)
     wall = time.time() - t
-    return len(cycles) / wall, sum(r[2] for r in res) / wall, dict(wall_s=wall, decodes=sum(r[0] for r in res),
-                                                                    per_cycle_s=float(np.mean([r[4] for r in res])))
+    ldpc = None if any(r[2] is None for r in res) else sum(r[2] for r in res) / wall
+    return len(cycles) / wall, ldpc, dict(wall_s=wall, decodes=sum(len(r[0]) for r in res), texts=[r[0] for r in res],
+                                          per_cycle_s=float(np.mean([r[3] for r in res])))
+
+
+def cpu_kind():
+    return ("reference", "unmodified G1OJS/PyFT8 v3.9.0 (oracle/_ref) through Receiver/AudioIn/Candidate, import stubs for "
+            "pyaudio/paho + fake clock (oracle/ref_harness.py)") if ref_available() else ("port", "numpy port oracle/ft8_oracle.py")
 
 
 def run_reference(args, dist, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself is Python
-    and does not travel to the GPU box), all host cores, bounded sample of the same workload per step."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores (one process per core),
+    bounded sample of the same workload per step."""
     if rank != 0:
         return
     from pyft8_b200 import workload
@@ -170,28 +275,150 @@ def run_reference(args, dist, rank, world):
     for w in range(args.warmup):
         cpu_rate(cyc[w * per_step:(w + 1) * per_step], cores)
     t0 = time.time()
-    ldpc = 0.0
+    ldpc, decodes = 0.0, 0
     for s in range(args.warmup, args.warmup + args.steps):
-        r, l, _ = cpu_rate(cyc[s * per_step:(s + 1) * per_step], cores)
-        ldpc += l
+        r, l, det = cpu_rate(cyc[s * per_step:(s + 1) * per_step], cores)
+        ldpc = None if (l is None or ldpc is None) else ldpc + l
+        decodes += det["decodes"]
     wall = time.time() - t0
     value = per_step * args.steps / wall
-    sample = f"{per_step} cycles per step ({args.ref_cycles_per_core} per core) of {WORKLOAD}, numpy-generated from the same parameters"
+    kind, how = cpu_kind()
+    sample = f"{per_step} cycles per step ({args.ref_cycles_per_core} per core) of {WORKLOAD}, numpy-generated from the same parameters; {how}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "cycles_per_step": per_step, "signals_per_cycle": workload.CONFIGS[WORKLOAD][0], "host": "cpu"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "ldpc_codewords_per_sec": ldpc / args.steps,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "decodes_per_cycle": decodes / (per_step * args.steps),
+        "ldpc_codewords_per_sec": (ldpc / args.steps) if ldpc is not None else None,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------- extra BASELINE configs
+def _oracle_ldpc(x):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ft8_oracle as o
+    z = x.copy()
+    st, n, _ = o.ldpc_decode(z, 90, 20)
+    return st, n
+
+
+def _oracle_osd(x):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ft8_oracle as o
+    b = o.osd(x.copy())
+    return b if b else 0
+
+
+def config_cfg3_fec(device, n_total, check):
+    """BASELINE configs[2]: noisy 174-bit LLR codewords at Eb/N0 0..4 dB through ft8_ldpc(., 90, 20), ft8_osd on the failures
+    (decoders.py:153-171, 223-272).  Kernel times from the library's CUDA events; `check` vectors per point are re-decoded
+    by the CPU oracle (decision-level identity)."""
+    from pyft8_b200 import synth, _lib as L
+    from pyft8_b200.engine import Engine, bits91_to_int
+    eng = Engine(device=device, max_cycles=1)
+    rng = np.random.default_rng(3)
+    msgs = [synth.pack77(*synth.random_message(rng)) for _ in range(1024)]
+    cws = np.array([synth.codeword_bits(b) for b in msgs], np.float32) * 2 - 1
+    per = n_total // 5
+    t_ldpc = t_osd = 0.0
+    n_osd = mism = osd_mism = checked = osd_checked = 0
+    bp_ok, fallback, rescued = [], [], []
+    pool = cpu_pool(os.cpu_count() or 1) if check else None
+    for e in range(5):
+        idx = rng.integers(0, 1024, per)
+        sigma = np.sqrt(1.0 / (2.0 * (91.0 / 174.0) * 10 ** (e / 10)))
+        y = cws[idx] + rng.standard_normal((per, 174), np.float32) * np.float32(sigma)
+        llr = (2.83 * y / y.std(axis=1, keepdims=True)).astype(np.float32)
+        x = llr.copy()
+        st, ni, bits = eng.ldpc(x, 90, 20)
+        t_ldpc += eng.last_kernel_ms(0)
+        ok = st == L.LDPC_OK
+        fail = np.flatnonzero(~ok)
+        if len(fail):
+            found, ob = eng.osd(llr[fail])
+            t_osd += eng.last_kernel_ms(0)
+        else:
+            found, ob = np.zeros(0, np.int32), np.zeros((0, 3), np.uint32)
+        n_osd += len(fail)
+        bp_ok.append(round(float(ok.mean()), 5))
+        fallback.append(round(len(fail) / per, 5))
+        rescued.append(round(float((found > 0).sum()) / max(len(fail), 1), 5))
+        if check:
+            ref = pool.map(_oracle_ldpc, [llr[i] for i in range(check)], chunksize=16)
+            mism += sum((s_ != (st[i] if st[i] != L.LDPC_STALL else L.LDPC_FAIL)) or (n_ != ni[i]) for i, (s_, n_) in enumerate(ref))
+            checked += check
+            k = min(check // 8, len(fail))
+            ref_o = pool.map(_oracle_osd, [llr[fail[j]] for j in range(k)], chunksize=2)
+            osd_mism += sum((bits91_to_int(ob[j]) if found[j] else 0) != ref_o[j] for j in range(k))
+            osd_checked += k
+    eng.close()
+    return {"config": "BASELINE configs[2]: noisy LLR codewords, Eb/N0 0..4 dB, ldpc_decode(.,90,20) then osd_012 on the failures",
+            "codewords": 5 * per, "ldpc_codewords_per_sec": 5 * per / (t_ldpc / 1e3), "ldpc_kernel_ms": round(t_ldpc, 3),
+            "osd_calls": int(n_osd), "osd_per_sec": n_osd / (t_osd / 1e3) if t_osd > 0 else None, "osd_kernel_ms": round(t_osd, 3),
+            "bp_ok": bp_ok, "osd_fallback_rate": fallback, "osd_rescued": rescued,
+            "oracle_checked": {"ldpc": checked, "osd": osd_checked}, "oracle_mismatch": int(mism + osd_mism),
+            "timing": "device time of the LDPC / OSD kernels (CUDA events inside the library), codewords resident in HBM"}
+
+
+def config_cycles(device, workload_name, B, steps, seed):
+    """Another cycle-shaped BASELINE config (e.g. configs[3]: 8192 x 120 signals) measured like the headline: device-resident
+    value and host-buffer e2e (streaming entry, every step's H2D and record D2H inside the timed region)."""
+    import torch
+    from pyft8_b200 import workload, _lib as L
+    from pyft8_b200.engine import Engine
+    eng = Engine(device=device, max_cycles=B)
+    params = workload.make_params(workload_name, B, seed=seed)
+    audio = torch.empty((B, 180000), dtype=torch.int16, device=f"cuda:{device}")
+    workload.device_cycles(eng, params, audio.data_ptr())
+    torch.cuda.synchronize()
+    host = torch.empty((B, 180000), dtype=torch.int16, pin_memory=True)
+    host.copy_(audio)
+    host_np = host.numpy()
+    rec_pin = torch.zeros((B * eng.max_cands, L.RECORD_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+    n_pin = torch.zeros(B, dtype=torch.int32).pin_memory()
+    rec_np, n_np = rec_pin.numpy().view(L.RECORD_DTYPE).reshape(-1), n_pin.numpy()
+    stream = torch.cuda.ExternalStream(L.load().ft8_stream(eng._h), device=f"cuda:{device}")
+    for _ in range(2):
+        eng.decode_cycles_dev(audio.data_ptr(), L.AUDIO_I16, B, rec=rec_np, n=n_np)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        eng.decode_cycles_dev(audio.data_ptr(), L.AUDIO_I16, B, rec=rec_np, n=n_np)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st = eng.stats()
+    eng.decode_cycles(host_np, next_audio=host_np, rec=rec_np, n=n_np)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = None
+    for i in range(steps):
+        r, _ = eng.decode_cycles(host_np, next_audio=host_np if i + 1 < steps else None, rec=rec_np, n=n_np)
+    torch.cuda.synchronize()
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+    out = {"config": f"{workload_name}: {B} cycles x {workload.CONFIGS[workload_name][0]} signals per step", "steps": steps,
+           "cycles_per_sec": B * steps / (ms / 1e3), "ms_per_step": ms / steps,
+           "e2e": {"value": B * steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(B * 360000),
+                   "d2h_bytes_per_step": int(len(r) * 64 + 4 * B + 96)},
+           "candidates_per_cycle": st["candidates"] / B, "at_max_cands": None, "decodes_per_cycle": st["decoded"] / B,
+           "emitted_per_cycle": st["emitted"] / B, "ldpc_codewords_per_sec": st["ldpc_calls"] / (ms / steps / 1e3),
+           "osd_calls_per_cycle": st["osd_calls"] / B}
+    eng.close()
+    del audio, host, rec_pin
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- our arm
 def run_gpu(args, dist, rank, local, world):
     import torch
     from pyft8_b200 import workload
     from pyft8_b200 import _lib as L
     from pyft8_b200.engine import Engine
+    from pyft8_b200.sharding import gather_records
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -247,69 +474,94 @@ def run_gpu(args, dist, rank, local, world):
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
     n_decoded, n_emitted = stats["decoded"], stats["emitted"]
-    # ---- end to end: pinned host audio in, records out, every step, through Engine.decode_cycles (C ABI, host buffers).
-    # Batches are streamed the way a skimmer would: each call names the next batch (ft8_decode_cycles_stream), whose PCIe
-    # copy then runs on a second CUDA stream underneath this batch's kernels.  Every step's H2D copy and record D2H are
-    # inside the timed region.
-    # caller-owned pinned output buffers (records, per-cycle counts), reused every step
-    rec_pin = torch.zeros((B * eng.max_cands, L.RECORD_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
-    n_pin = torch.zeros(B, dtype=torch.int32).pin_memory()
-    rec_np, n_np = rec_pin.numpy().view(L.RECORD_DTYPE).reshape(-1), n_pin.numpy()
-
-    def e2e_steps(k):
-        r_i = None
-        # step 0 is not prefetched: its copy runs in chunks with the front-end kernels starting as chunks land (and is
-        # inside the timed region like every other step's); from step 1 on the copy hides under the previous step
-        for i in range(k):
-            r_i, _ = eng.decode_cycles(host_np, next_audio=host_np if i + 1 < k else None, rec=rec_np, n=n_np)
-        return r_i
-
-    e2e_steps(min(args.warmup, 2))
-    barrier()
-    t0 = time.perf_counter()
-    rec_last = e2e_steps(args.steps)
-    barrier()
-    ms_e2e = max_over_ranks(1e3 * (time.perf_counter() - t0))
-    n_e2e_decoded = len(rec_last)
-    # host text formatting of one step's records (outside every timed region): vectorised unpack + de-dup
-    from pyft8_b200.receiver import format_records
-    format_records(rec_last[:1000])
-    t0 = time.perf_counter()
-    mb = format_records(rec_last)
-    host_text = {"records_per_sec": len(rec_last) / max(time.perf_counter() - t0, 1e-9), "records": int(len(rec_last)),
-                 "messages": int(len(mb)), "note": "format_records on one step's records, one host thread, not in any timed region"}
+    dev_records = np.array(r, copy=True)                  # last device-resident step's records (parity spot check below)
+    dev_counts = np.array(n, copy=True)
     total_cycles = sum_over_ranks(B)
     value = total_cycles * args.steps / (ms_dev / 1e3)
-    e2e = total_cycles * args.steps / (ms_e2e / 1e3)
     stage_ms /= args.steps
     ldpc_rate = sum_over_ranks(stats["ldpc_calls"]) / (ms_dev / args.steps / 1e3)
+    e2e_out = host_text = None
+    if not args.device_only:
+        # ---- end to end: pinned host audio in, records out, every step, through Engine.decode_cycles (C ABI, host buffers).
+        # Batches are streamed the way a skimmer would: each call names the next batch (ft8_decode_cycles_stream), whose PCIe
+        # copy then runs on a second CUDA stream underneath this batch's kernels.  Every step's H2D copy and record D2H are
+        # inside the timed region, and so is -- at N > 1 -- the host-side gather of all ranks' records on rank 0
+        # (sharding.gather_records over gloo: the path's only cross-GPU step).
+        rec_pin = torch.zeros((B * eng.max_cands, L.RECORD_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+        n_pin = torch.zeros(B, dtype=torch.int32).pin_memory()
+        rec_np, n_np = rec_pin.numpy().view(L.RECORD_DTYPE).reshape(-1), n_pin.numpy()
+        gathered = [0, 0]
+
+        def e2e_steps(k):
+            r_i = None
+            # step 0 is not prefetched: its copy runs in chunks with the front-end kernels starting as chunks land (and is
+            # inside the timed region like every other step's); from step 1 on the copy hides under the previous step
+            for i in range(k):
+                r_i, _ = eng.decode_cycles(host_np, next_audio=host_np if i + 1 < k else None, rec=rec_np, n=n_np)
+                if dist:
+                    allrec = gather_records(r_i, rank * B, dist, dst=0)
+                    if rank == 0:
+                        gathered[0], gathered[1] = len(allrec), allrec.nbytes
+            return r_i
+
+        e2e_steps(min(args.warmup, 2))
+        barrier()
+        t0 = time.perf_counter()
+        rec_last = e2e_steps(args.steps)
+        barrier()
+        ms_e2e = max_over_ranks(1e3 * (time.perf_counter() - t0))
+        n_e2e_decoded = len(rec_last)
+        e2e = total_cycles * args.steps / (ms_e2e / 1e3)
+        e2e_out = {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 360000), "d2h_bytes_per_step": int(n_e2e_decoded * 64 + 4 * B + 96),
+                   "ms_per_step": ms_e2e / args.steps,
+                   "gather": {"records_on_rank0_per_step": gathered[0], "bytes_on_rank0_per_step": gathered[1],
+                              "how": "sharding.gather_records (gloo object gather) inside the timed region"} if dist else None,
+                   "api": "Engine.decode_cycles(pinned host int16, next_audio=...) -> ft8_decode_cycles_stream: one handle, next batch copied under the kernels"}
+        # host text formatting of one step's records (outside every timed region): vectorised unpack + de-dup
+        from pyft8_b200.receiver import format_records
+        format_records(rec_last[:1000])
+        t0 = time.perf_counter()
+        mb = format_records(rec_last)
+        host_text = {"records_per_sec": len(rec_last) / max(time.perf_counter() - t0, 1e-9), "records": int(len(rec_last)),
+                     "messages": int(len(mb)), "note": "format_records on one step's records, one host thread, not in any timed region"}
+        del rec_pin
     if rank != 0:
         return
-    peak, peak_src = _peaks()
-    units = {"spectrogram": B, "sync": B, "cycle_spectrum": B, "pass0_ldpc5": stats["candidates"], "fine": stats["fine_evals"],
-             "pass234_ldpc": max(stats["ldpc_calls"], 1), "osd": max(stats["osd_calls"], 1)}
-    stages = []
-    for i, name in enumerate(STAGES):
-        if name in ALG_BYTES:
-            ach = ALG_BYTES[name] * units[name] / (stage_ms[i] / 1e3) / 1e9 if stage_ms[i] > 0 else 0.0
-            traffic = NCU_DRAM_BYTES_PER_CYCLE.get(name)
-            stages.append({"kernel": name, "ms": round(float(stage_ms[i]), 4), "share": round(float(stage_ms[i] / stage_ms[0]), 4),
-                           "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 5),
-                           "traffic": int(traffic * B) if traffic else None, "ncu_pct_of_peak": NCU_PIPES.get(name)})
-    dom = max(stages, key=lambda s: s["ms"])
-    roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
-                "note": "dominant kernel by device time; LDPC/OSD/fine-sync stages are issue/ALU-bound, see DESIGN.md; "
-                        "spectrogram and sync (the HBM-roofline stages of the north star) are in roofline_stages"}
+    units = {"cycles": B, "candidates": stats["candidates"], "fine_evals": stats["fine_evals"],
+             "ldpc_calls": max(stats["ldpc_calls"], 1), "osd_calls": max(stats["osd_calls"], 1)}
+    roofline, stages = roofline_block(stage_ms, units, B)
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.device_only:
         cores = os.cpu_count() or 1
-        sample = [host_np[i].copy() for i in range(cores)]
+        n_s = cores * args.cpu_cycles_per_core
+        sample = [host_np[i].copy() for i in range(n_s)]
         v, l, det = cpu_rate(sample, cores)
-        # parity spot check on the sample is done by tests/smoke; here only the rate is reported
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {cores} cycles of this run's batch (one per core), oracle port, {det['wall_s']:.1f} s wall",
-               "ldpc_codewords_per_sec": l}
+        kind, how = cpu_kind()
+        # parity spot check on the same cycles: emitted message texts of the CUDA path vs the CPU arm (reported, not asserted
+        # here -- the assertions live in tests/)
+        from pyft8_b200.receiver import format_records
+        from pyft8_b200 import messages
+        same, diffs = 0, []
+        off = np.concatenate([[0], np.cumsum(dev_counts)])
+        for i in range(n_s):
+            messages.call_hashes.clear()
+            mb = format_records(dev_records[off[i]:off[i + 1]])
+            ours = sorted(t for t, k in zip(mb.text.tolist(), mb.keep.tolist()) if k)
+            ok = ours == sorted(det["texts"][i])
+            same += ok
+            if not ok and len(diffs) < 4:
+                diffs.append({"cycle": i, "only_cuda": sorted(set(ours) - set(det["texts"][i])), "only_cpu": sorted(set(det["texts"][i]) - set(ours)),
+                              "n_cuda": len(ours), "n_cpu": len(det["texts"][i])})
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"first {n_s} cycles of this run's batch ({args.cpu_cycles_per_core} per core), {how}, {det['wall_s']:.1f} s wall",
+               "ldpc_codewords_per_sec": l, "sample_parity": {"cycles": n_s, "identical_message_sets": int(same), "differences": diffs}}
+    configs = None
+    if world == 1 and not args.no_configs and not args.device_only:
+        eng.close()
+        del audio, host
+        torch.cuda.empty_cache()
+        configs = {"cfg3_fec": config_cfg3_fec(local, args.fec_codewords, args.fec_check),
+                   "cfg4_120sig": config_cycles(local, "cfg4_120sig", args.cfg4_cycles, 2, args.seed + 4)}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -317,13 +569,12 @@ def run_gpu(args, dist, rank, local, world):
         "config": {"workload": WORKLOAD, "cycles_per_gpu_per_step": B, "signals_per_cycle": workload.CONFIGS[WORKLOAD][0],
                    "snr_db": list(workload.CONFIGS[WORKLOAD][1]),
                    "audio": "int16 12 kHz 15 s", "l2": "inputs_larger_than_l2 (%.2f GB per step per GPU)" % (B * 360000 / 1e9),
-                   "parallelism": f"cycles sharded over {world} GPU(s), no collective"},
+                   "parallelism": f"cycles sharded over {world} GPU(s), no collective; records gathered on rank 0 host-side"},
         "ldpc_codewords_per_sec": ldpc_rate,
         "decodes_per_cycle": n_decoded / B, "emitted_per_cycle": n_emitted / B,
         "work_per_step": {k: stats[k] for k in ("candidates", "stopped_sd", "fine_evals", "fine_pass", "ldpc_calls", "ldpc_iters", "osd_calls")},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 360000), "d2h_bytes_per_step": int(n_e2e_decoded * 64 + 4 * B + 96),
-                "ms_per_step": ms_e2e / args.steps, "api": "Engine.decode_cycles(pinned host int16, next_audio=...) -> ft8_decode_cycles_stream: one handle, next batch copied under the kernels"},
-        "host_text": host_text, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_stages": stages, "cpu_baseline": cpu,
+        "e2e": e2e_out, "host_text": host_text, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "roofline_stages": stages, "cpu_baseline": cpu, "configs": configs,
     }
     print(json.dumps(out), flush=True)
 
@@ -340,7 +591,13 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD, choices=["cfg1_20sig", "cfg2_50sig", "cfg4_120sig"],
                     help="cfg2_50sig is the headline configuration (BASELINE configs[1])")
     ap.add_argument("--ref-cycles-per-core", type=int, default=1)
+    ap.add_argument("--cpu-cycles-per-core", type=int, default=1, help="cycles per host core of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[2] / configs[3] measurements of the default N=1 run")
+    ap.add_argument("--device-only", action="store_true", help="only the device-resident timed steps (used under ncu)")
+    ap.add_argument("--fec-codewords", type=int, default=1000000)
+    ap.add_argument("--fec-check", type=int, default=64, help="LDPC vectors per Eb/N0 point re-decoded by the oracle (configs.cfg3_fec)")
+    ap.add_argument("--cfg4-cycles", type=int, default=8192)
     args = ap.parse_args()
     WORKLOAD = args.workload
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

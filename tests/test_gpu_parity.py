@@ -235,17 +235,37 @@ def test_sync_same_input_identical_candidates(eng, name, golden_cycles):
     assert np.array_equal(f0o[0, :int(no[0])], fo2) and np.array_equal(h0o[0, :int(no[0])], ho2)
 
 
+# Candidates that differ between the GPU's own grid and the reference's, per golden cycle: measured on B200 and pinned
+# (profiles/r02_parity_large.md).  Round 1 allowed "<= 4" for near-ties of the coarse score without recording
+# them; the recorded difference is empty for all five cycles, so the bound is now 0.
+SYNC_OWN_GRID_MAX_DIFF = {"test_08": 0, "test_09": 0, "syn20": 0, "syn50": 0, "syn120": 0}     # measured: no difference at all
+
+
 def test_sync_own_grid_and_topk_pressure(eng, golden_cycles):
-    """End-to-end S1+S2 on the GPU's own grid: same candidate SET as the reference up to near-ties."""
+    """End-to-end S1+S2 on the GPU's own grid: same candidate SET as the reference up to near-ties (SURVEY H11);
+    the actual differences are recorded, not just bounded."""
+    import json, os
+    from conftest import ROOT
+    rep = {}
     for name in ALL_CYCLES:
         audio, g = golden_cycles[name]
         f0, h0, sc, n, _ = eng.sync(eng.spectrogram(audio)[0], want_payload=False)
         n = int(n[0])
         got = set(zip(f0[0, :n].tolist(), h0[0, :n].tolist()))
         want = set(zip(g["cand_f0"].tolist(), g["cand_h0"].tolist()))
-        assert len(got ^ want) <= 4, (name, sorted(got ^ want))
+        ref_score = {(f, h): float(s) for f, h, s in zip(g["cand_f0"].tolist(), g["cand_h0"].tolist(), g["cand_score"].tolist())}
+        gpu_score = {(f, h): float(s) for f, h, s in zip(f0[0, :n].tolist(), h0[0, :n].tolist(), sc[0, :n].tolist())}
+        rep[name] = {"n_ref": len(want), "n_gpu": n,
+                     "only_gpu": [[f, h, round(gpu_score[(f, h)], 3)] for f, h in sorted(got - want)],
+                     "only_ref": [[f, h, round(ref_score[(f, h)], 3)] for f, h in sorted(want - got)]}
         assert np.all(np.diff(sc[0, :n]) <= 0)                                 # sorted by score, descending
         assert len(set(f0[0, :n].tolist())) == n                                # at most one candidate per f0 bin
+    print("[sync_own_grid] " + json.dumps(rep))
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        json.dump(rep, open(os.path.join(out, "sync_own_grid_diff.json"), "w"))
+    for name, r in rep.items():
+        assert len(r["only_gpu"]) + len(r["only_ref"]) <= SYNC_OWN_GRID_MAX_DIFF[name], (name, r)
 
 
 def test_sync_empty_and_flat_grids(eng):
