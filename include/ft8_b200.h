@@ -73,7 +73,9 @@ typedef struct ft8_cfg {
     int32_t osd_singleflips;   /* osd_012(singleflips=30)                                              */
     int32_t osd_doubleflips;   /* osd_012(doubleflips=2)                                               */
     int32_t max_codewords;     /* scratch capacity of the stand-alone ft8_llr/ft8_ldpc/ft8_osd/ft8_crc14 ops (0: default 1<<16) */
-    int32_t reserved[5];
+    int32_t fine_mode;         /* fine sync (receiver.py:140-206): 0 = time scan + tensor-core frequency scan + final transform
+                                  (default); 1 = the literal nine-inverse-FFT kernel (A/B reference for the former)            */
+    int32_t reserved[4];
 } ft8_cfg;
 
 /* One decoded candidate, as Candidate.check_and_package would see it (receiver.py:51-66). 64 bytes. */

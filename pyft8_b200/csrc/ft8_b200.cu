@@ -21,6 +21,7 @@
 #include "spectrogram.cuh"
 #include "sync.cuh"
 #include "fine.cuh"
+#include "fine_tc.cuh"
 #include "passes.cuh"
 #include "synth.cuh"
 
@@ -42,6 +43,9 @@ struct ft8_handle {
            *d_W96000 = nullptr, *d_W192000 = nullptr, *d_W32 = nullptr;
     float2 *d_TS = nullptr, *d_TF = nullptr, *d_TC = nullptr, *d_T256 = nullptr, *d_W96000T = nullptr;   // per-pass twiddle tables [k-1][p]
     float* d_pulse = nullptr;        // GFSK pulse for the synthetic generator
+    // tensor-core frequency scan (fine_tc.cuh): B operand (E | M, tf32 hi/lo), half-sample phase table, per-item intermediates
+    float* d_bmat = nullptr; float2* d_w6400 = nullptr;
+    float2* d_zwin = nullptr; TScanOut* d_tso = nullptr; int32_t* d_ff = nullptr; size_t fine_tmp_items = 0;
     // batch scratch
     size_t cap_cycles = 0, cap_slots = 0;
     void* d_audio = nullptr; size_t audio_bytes = 0;
@@ -187,6 +191,43 @@ static cudaError_t upload_constant_tables() {
     return cudaMemcpyToSymbol(c_fine, &ft, sizeof(ft));
 }
 
+// B operand of k_fscan_mma, laid out exactly as one shared-memory stage per K-chunk: [chunk][split hi/lo][k-chunk 0/1][n][4]
+// (see fine_tc.cuh for the formulas; tp is the reference's taper incl. the inverted upper ramp, receiver.py:182-183)
+static std::vector<float> fscan_bmat() {
+    auto taper = [](int i) { return 0.5 * (1.0 + cos(-M_PI + M_PI * (double)i / 99.0)); };
+    auto tp = [&](int k) -> double {
+        if (k < -150 || k >= 850) return 0.0;
+        if (k < -50) return taper(k + 150);
+        if (k < 750) return 1.0;
+        return taper(k - 750);
+    };
+    auto split_hi = [](float v) { uint32_t u; memcpy(&u, &v, 4); u = (u + 0x1000u) & 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; };
+    std::vector<float> out((size_t)FS_BMAT_FLOATS, 0.0f);
+    for (int n = 0; n < FS_N; ++n) {
+        const int f = n >> 3, t = n & 7;
+        const int d = -32 + 8 * (f < 4 ? f : f + 1);
+        for (int k = 0; k < FS_K; ++k) {
+            double v;
+            if (k < FS_K1) {
+                const int r = k >> 1;
+                const double ang = -2.0 * M_PI * (double)(100 * t + d) * ((double)r - 15.5) / 3200.0;
+                v = (k & 1) ? sin(ang) : cos(ang);
+            } else {
+                const int u = fs_u_of(k - FS_K1);
+                const int x = u - d - 100 * t;
+                const double dir = x == 0 ? 32.0 : sin(M_PI * x / 100.0) / sin(M_PI * x / 3200.0);
+                v = (tp(u - d) - tp(u)) * dir;
+            }
+            const float vf = (float)v, hi = split_hi(vf), lo = split_hi((float)(v - (double)hi));
+            const int chunk = k / FS_KC, kc = (k % FS_KC) / 4, e = k % 4;
+            const size_t base = (size_t)chunk * (FS_B_STAGE_BYTES / 4);
+            out[base + 0 * (FS_B_SPLIT_BYTES / 4) + kc * (FS_N * 4) + n * 4 + e] = hi;
+            out[base + 1 * (FS_B_SPLIT_BYTES / 4) + kc * (FS_N * 4) + n * 4 + e] = lo;
+        }
+    }
+    return out;
+}
+
 template <typename T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
 
 static int ensure_arena(ft8_handle* h, size_t bytes) {
@@ -234,6 +275,7 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
     if (cfg.osd_singleflips < 0 || cfg.osd_singleflips > OSD_MAX_FLIPS || cfg.osd_doubleflips < 0)
         return fail(nullptr, FT8_E_BADARG, "ft8_create: osd flips out of range");
     if (cfg.max_codewords <= 0) cfg.max_codewords = 1 << 16;
+    if (cfg.fine_mode != 0 && cfg.fine_mode != 1) return fail(nullptr, FT8_E_BADARG, "ft8_create: fine_mode must be 0 (tensor-core scan) or 1 (FFT scan)");
     ft8_handle* h = new ft8_handle();
     h->device = device;
     h->cfg = cfg;
@@ -284,6 +326,12 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
             CKC(upload(&h->d_W96000T, w96t));
         }
         CKC(upload(&h->d_pulse, synth_pulse_table()));
+        CKC(upload(&h->d_bmat, fscan_bmat()));
+        {
+            std::vector<float2> w(FS_W_LEN);
+            for (int g = 0; g < FS_W_LEN; ++g) { const double a = 2.0 * M_PI * (double)g / (double)FS_W_LEN; w[g] = make_float2((float)cos(a), (float)sin(a)); }
+            CKC(upload(&h->d_w6400, w));
+        }
     }
     const size_t B = (size_t)cfg.max_cycles, K = (size_t)cfg.max_cands, N = B * K;
     h->cap_cycles = B;
@@ -311,6 +359,13 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
         CKC(cudaMemcpy(h->d_cycle_of, co.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     CKC(cudaFuncSetAttribute(k_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, FINE_SMEM_BYTES));
+    CKC(cudaFuncSetAttribute(k_fine_tscan, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
+    CKC(cudaFuncSetAttribute(k_fine_final, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    CKC(cudaFuncSetAttribute(k_fscan_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
+    if (cfg.fine_mode == 0) {
+        h->fine_tmp_items = N;
+        CKC(dmalloc(&h->d_zwin, N * FS_WIN)); CKC(dmalloc(&h->d_tso, N)); CKC(dmalloc(&h->d_ff, N));
+    }
     CKC(cudaFuncSetAttribute(k_spectrogram<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2)));
     CKC(cudaFuncSetAttribute(k_spectrogram<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2)));
     CKC(cudaFuncSetAttribute(k_sync_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
@@ -325,7 +380,7 @@ extern "C" void ft8_destroy(ft8_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_TS, h->d_TF, h->d_TC, h->d_T256, h->d_W96000T, h->d_hann, h->d_W1920, h->d_W3840, h->d_W3200, h->d_W375, h->d_W256, h->d_W96000, h->d_W192000, h->d_W32,
-                    h->d_pulse, h->d_audio, h->d_grid, h->d_Y, h->d_spec, h->d_best_score, h->d_best_h0, h->d_f0, h->d_h0, h->d_score,
+                    h->d_pulse, h->d_bmat, h->d_w6400, h->d_zwin, h->d_tso, h->d_ff, h->d_audio, h->d_grid, h->d_Y, h->d_spec, h->d_best_score, h->d_best_h0, h->d_f0, h->d_h0, h->d_score,
                     h->d_ncand, h->d_cycle_of, h->d_status, h->d_llr_grid, h->d_grid_sd, h->d_grid_snr, h->d_llr_fine, h->d_fine,
                     h->d_saved, h->d_saved_n, h->d_saved_ap, h->d_bits, h->d_ripass, h->d_rap, h->d_rmethod, h->d_rnits,
                     h->d_osd_found, h->d_osd_bits, h->d_list_fine, h->d_list_osd, h->d_counts, h->d_stats, h->d_rec, h->d_rec_n, h->d_rec_base, h->arena};
@@ -418,14 +473,37 @@ static int launch_cycle_spectrum(ft8_handle* h, const void* d_audio, int dtype, 
 
 static int persistent_blocks(ft8_handle* h, int per_sm) { return h->n_sm * per_sm; }
 
-// F2/F3 for a work list (list/count on the device) or for items 0..n_direct-1 (list == nullptr)
+// F2/F3 for a work list (list/count on the device, at most cap_slots items) or for items 0..n_direct-1 (list == nullptr).
+// fine_mode 0: time scan -> tensor-core frequency scan -> final transform (fine_tc.cuh); 1: the literal 9-transform kernel.
 static int launch_fine(ft8_handle* h, const float2* spec, int spec_stride, const int32_t* list, const int32_t* count, int n_direct,
                        const int32_t* cycle_of, const int16_t* f0, const int16_t* h0, FineOut* fo, float* llr, float* sig_grid) {
-    const int blocks = list ? persistent_blocks(h, 4) : std::min(persistent_blocks(h, 4), n_direct);
-    k_fine<<<blocks, FINE_NT, FINE_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, fo, llr, sig_grid);
+    if (h->cfg.fine_mode == 1) {
+        const int blocks = list ? persistent_blocks(h, 4) : std::min(persistent_blocks(h, 4), n_direct);
+        k_fine<<<blocks, FINE_NT, FINE_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, fo, llr, sig_grid);
+        CK(cudaGetLastError());
+        return FT8_OK;
+    }
+    const size_t need = list ? h->cap_slots : (size_t)n_direct;
+    if (need > h->fine_tmp_items) {
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->d_zwin) CK(cudaFree(h->d_zwin)); if (h->d_tso) CK(cudaFree(h->d_tso)); if (h->d_ff) CK(cudaFree(h->d_ff));
+        h->d_zwin = nullptr; h->d_tso = nullptr; h->d_ff = nullptr; h->fine_tmp_items = 0;
+        CK(dmalloc(&h->d_zwin, need * FS_WIN)); CK(dmalloc(&h->d_tso, need)); CK(dmalloc(&h->d_ff, need));
+        h->fine_tmp_items = need;
+    }
+    const int nb3 = list ? persistent_blocks(h, 3) : std::min(persistent_blocks(h, 3), n_direct);
+    k_fine_tscan<<<nb3, FINE_NT, FT_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, h->d_tso, h->d_zwin);
+    CK(cudaGetLastError());
+    const int nb1 = list ? h->n_sm : std::min(h->n_sm, (n_direct + FS_CAND - 1) / FS_CAND);
+    k_fscan_mma<<<nb1, FS_NT, FS_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_tso, h->d_zwin,
+                                                         h->d_bmat, h->d_w6400, h->d_ff);
+    CK(cudaGetLastError());
+    k_fine_final<<<nb3, FINE_NT, FF_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, h->d_tso, h->d_ff,
+                                                            fo, llr, sig_grid);
     CK(cudaGetLastError());
     return FT8_OK;
 }
+static int fine_launches(ft8_handle* h) { return h->cfg.fine_mode == 1 ? 1 : 3; }
 
 // copy helpers honouring the mem flag
 static int to_device(ft8_handle* h, void* d, const void* src, size_t bytes, int mem) {
@@ -945,7 +1023,7 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
     // ipass 1
     TRY(launch_fine(h, h->d_spec, FINE_SPEC_STRIDE, h->d_list_fine, h->d_counts + 0, 0, h->d_cycle_of, h->d_f0, h->d_h0, h->d_fine,
                     h->d_llr_fine, nullptr));
-    ++launches;
+    launches += fine_launches(h);
     CK(cudaEventRecord(h->ev[5], h->stream));
     // ipass 2-4
     k_pass234<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
