@@ -1141,6 +1141,14 @@ extern "C" int ft8_debug_fft(ft8_handle* h, int n, int inverse, const float* in,
     return FT8_OK;
 }
 
+#ifdef FS_PROFILE
+extern "C" int ft8_debug_fs_prof(unsigned long long* out16, int reset) {
+    cudaMemcpyFromSymbol(out16, ft8::g_fs_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(ft8::g_fs_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 #ifdef FINE_PROFILE
 // debug build only: read (and optionally reset) the k_fine phase counters
 extern "C" int ft8_debug_fine_prof(unsigned long long* out16, int reset) {

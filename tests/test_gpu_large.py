@@ -164,3 +164,30 @@ def test_cfg3_fec_20k_codewords_vs_oracle(pool):
     assert tot_llr_bad <= 5, rep                           # post-LDPC llr within 2e-3 (fp32 tanh/atanh chains; r01: 2 in 50 000)
     bp = [p["bp_ok"] for p in rep["points"]]
     assert all(b1 >= b0 for b0, b1 in zip(bp, bp[1:])) and bp[-1] > 0.9, rep     # monotone in Eb/N0: the sweep is a sweep
+
+
+def test_tensor_core_scan_equals_nine_fft_kernel():
+    """fine_mode 0 (time scan + tcgen05 3xTF32 frequency scan + final transform) against fine_mode 1 (the literal nine inverse
+    FFTs of receiver.py:147-159) on 256 cycles: every record field identical, incl. both tweaks of every decoded candidate."""
+    import torch
+    B = 256
+    params = workload.make_params("cfg2_50sig", B, seed=99)
+    audio, recs = None, {}
+    for mode in (1, 0):
+        eng = Engine(max_cycles=B, fine_mode=mode)
+        if audio is None:
+            audio = torch.empty((B, 180000), dtype=torch.int16, device="cuda:0")
+            workload.device_cycles(eng, params, audio.data_ptr())
+            torch.cuda.synchronize()
+        r, n = eng.decode_cycles_dev(audio.data_ptr(), L.AUDIO_I16, B)
+        recs[mode] = (np.array(r, copy=True), np.array(n, copy=True), eng.stats())
+        eng.close()
+    (r1, n1, s1), (r0, n0, s0) = recs[1], recs[0]
+    assert np.array_equal(n0, n1) and len(r0) == len(r1) > 10 * B
+    diff = {k: int(np.sum(np.any(np.atleast_2d((r0[k] != r1[k]).T), axis=0))) for k in
+            ("bits91", "cycle", "cand", "ipass", "ap", "method", "ttweak", "ftweak", "nsync", "snr", "emitted", "n_its")}
+    rep = dict(records=len(r0), field_mismatches=diff, fine_pass=[s0["fine_pass"], s1["fine_pass"]], fine_evals=s0["fine_evals"])
+    _report("fine_tc_vs_fft", rep)
+    assert not any(diff.values()), rep
+    # candidates that pass the Costas count (nsync > 6): a frequency-tweak near-tie can move one across the threshold
+    assert abs(s0["fine_pass"] - s1["fine_pass"]) <= 2, rep

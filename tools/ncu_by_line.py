@@ -51,7 +51,9 @@ for i in range(n):
 ti, ts = sum(agg_i.values()), sum(agg_s.values())
 print(f"{kname[:80]}: {len(sass)} SASS instrs, {len(lines)} with line info; total warp-instr {ti}, samples {ts}")
 src_cache = {}
-for key, v in sorted(agg_s.items(), key=lambda x: -x[1])[:top]:
+by_inst = os.environ.get("BY_INST") == "1"       # BY_INST=1: rank lines by executed instructions instead of stall samples
+for key, v in sorted((agg_i if by_inst else agg_s).items(), key=lambda x: -x[1])[:top]:
+    v = agg_s[key]
     txt = ""
     if key:
         for d in ("pyft8_b200/csrc", "include"):
