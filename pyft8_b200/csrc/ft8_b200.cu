@@ -491,8 +491,9 @@ static int launch_fine(ft8_handle* h, const float2* spec, int spec_stride, const
         CK(dmalloc(&h->d_zwin, need * FS_WIN)); CK(dmalloc(&h->d_tso, need)); CK(dmalloc(&h->d_ff, need));
         h->fine_tmp_items = need;
     }
-    const int nb3 = list ? persistent_blocks(h, 3) : std::min(persistent_blocks(h, 3), n_direct);
-    k_fine_tscan<<<nb3, FINE_NT, FT_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, h->d_tso, h->d_zwin);
+    const int nbt = list ? persistent_blocks(h, FT_CTAS) : std::min(persistent_blocks(h, FT_CTAS), n_direct);
+    const int nb3 = list ? persistent_blocks(h, FF_CTAS) : std::min(persistent_blocks(h, FF_CTAS), n_direct);
+    k_fine_tscan<<<nbt, FINE_NT, FT_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, h->d_tso, h->d_zwin);
     CK(cudaGetLastError());
     const int nb1 = list ? h->n_sm : std::min(h->n_sm, (n_direct + FS_CAND - 1) / FS_CAND);
     k_fscan_mma<<<nb1, FS_NT, FS_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_tso, h->d_zwin,
