@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -337,7 +338,13 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
     h->cap_cycles = B;
     h->cap_slots = N;
     CKC(dmalloc(&h->d_grid, B * GRID_ROWS * GRID_COLS));
-    h->y_cycles = std::min<size_t>(B, 1024);   // four-step scratch: 768 KB per cycle
+    // four-step scratch Y: 768 KB per cycle, written by k_cs_cols and read back by k_cs_rows, in chunks of up to 1024 cycles.
+    // Smaller, L2-resident chunks were measured and are SLOWER: 3.18 ms per 4096 cycles at 1024, 3.50 at 256,
+    // 3.88 at 128, 4.20 at 64, 5.00 at 32 (profiles/r02_experiments.md) -- both kernels sit on the L1/shared data pipe, not on
+    // HBM, so the 3x DRAM traffic costs nothing while small grids lose to tail effects.  FT8_Y_CYCLES overrides for experiments.
+    size_t ych = 1024;
+    if (const char* e = getenv("FT8_Y_CYCLES")) ych = (size_t)std::max(1, atoi(e));
+    h->y_cycles = std::min<size_t>(B, ych);
     CKC(dmalloc(&h->d_Y, h->y_cycles * CS_N));
     CKC(dmalloc(&h->d_spec, B * FINE_SPEC_STRIDE));
     CKC(dmalloc(&h->d_best_score, B * N_F0 * SY_HS));
