@@ -418,7 +418,7 @@ def run_gpu(args, dist, rank, local, world):
     from pyft8_b200 import workload
     from pyft8_b200 import _lib as L
     from pyft8_b200.engine import Engine
-    from pyft8_b200.sharding import gather_records
+    from pyft8_b200.sharding import ShmRecordGather
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -486,22 +486,27 @@ def run_gpu(args, dist, rank, local, world):
         # Batches are streamed the way a skimmer would: each call names the next batch (ft8_decode_cycles_stream), whose PCIe
         # copy then runs on a second CUDA stream underneath this batch's kernels.  Every step's H2D copy and record D2H are
         # inside the timed region, and so is -- at N > 1 -- the host-side gather of all ranks' records on rank 0
-        # (sharding.gather_records over gloo: the path's only cross-GPU step).
+        # (sharding.ShmRecordGather: the path's only cross-GPU step).
         rec_pin = torch.zeros((B * eng.max_cands, L.RECORD_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
         n_pin = torch.zeros(B, dtype=torch.int32).pin_memory()
         rec_np, n_np = rec_pin.numpy().view(L.RECORD_DTYPE).reshape(-1), n_pin.numpy()
         gathered = [0, 0]
+        shm = ShmRecordGather(dist, B * eng.max_cands, L.RECORD_DTYPE, tag=os.environ.get("MASTER_PORT", "0")) if dist else None
+        shm_pinned = shm.pin() if shm else None
 
         def e2e_steps(k):
             r_i = None
             # step 0 is not prefetched: its copy runs in chunks with the front-end kernels starting as chunks land (and is
             # inside the timed region like every other step's); from step 1 on the copy hides under the previous step
             for i in range(k):
-                r_i, _ = eng.decode_cycles(host_np, next_audio=host_np if i + 1 < k else None, rec=rec_np, n=n_np)
-                if dist:
-                    allrec = gather_records(r_i, rank * B, dist, dst=0)
+                # N > 1: the records are copied back straight into this rank's shared-memory slot (pinned with cudaHostRegister)
+                out = shm.slot_array() if shm else rec_np
+                r_i, _ = eng.decode_cycles(host_np, next_audio=host_np if i + 1 < k else None, rec=out, n=n_np)
+                if shm:
+                    shm.publish_inplace(len(r_i), rank * B)
+                    parts = shm.collect()                 # barrier; rank 0 now sees every rank's records of this step
                     if rank == 0:
-                        gathered[0], gathered[1] = len(allrec), allrec.nbytes
+                        gathered[0], gathered[1] = sum(len(p) for p in parts), sum(p.nbytes for p in parts)
             return r_i
 
         e2e_steps(min(args.warmup, 2))
@@ -514,8 +519,8 @@ def run_gpu(args, dist, rank, local, world):
         e2e = total_cycles * args.steps / (ms_e2e / 1e3)
         e2e_out = {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 360000), "d2h_bytes_per_step": int(n_e2e_decoded * 64 + 4 * B + 96),
                    "ms_per_step": ms_e2e / args.steps,
-                   "gather": {"records_on_rank0_per_step": gathered[0], "bytes_on_rank0_per_step": gathered[1],
-                              "how": "sharding.gather_records (gloo object gather) inside the timed region"} if dist else None,
+                   "gather": {"records_on_rank0_per_step": gathered[0], "bytes_on_rank0_per_step": gathered[1], "segments_pinned": shm_pinned,
+                              "how": "sharding.ShmRecordGather: per-rank shared-memory segments + one gloo barrier per step, inside the timed region"} if dist else None,
                    "api": "Engine.decode_cycles(pinned host int16, next_audio=...) -> ft8_decode_cycles_stream: one handle, next batch copied under the kernels"}
         # host text formatting of one step's records (outside every timed region): vectorised unpack + de-dup
         from pyft8_b200.receiver import format_records
@@ -525,6 +530,8 @@ def run_gpu(args, dist, rank, local, world):
         host_text = {"records_per_sec": len(rec_last) / max(time.perf_counter() - t0, 1e-9), "records": int(len(rec_last)),
                      "messages": int(len(mb)), "note": "format_records on one step's records, one host thread, not in any timed region"}
         del rec_pin
+        if shm:
+            shm.close()
     if rank != 0:
         return
     units = {"cycles": B, "candidates": stats["candidates"], "fine_evals": stats["fine_evals"],

@@ -113,6 +113,50 @@ def test_gather_records_world_size_2_gloo(tmp_path):
     assert "GATHER_OK" in outs[0]
 
 
+_SHM_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch.distributed as dist
+from pyft8_b200 import _lib as L
+from pyft8_b200.sharding import ShmRecordGather
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+r = dist.get_rank()
+g = ShmRecordGather(dist, capacity=16, dtype=L.RECORD_DTYPE, tag="t" + sys.argv[2])
+ok = True
+for step in range(3):
+    rec = np.zeros(3 + r + step, L.RECORD_DTYPE)
+    rec["cycle"] = np.arange(len(rec)) % 2
+    rec["cand"] = 100 * r + step
+    if step == 1:                                  # in-place form: records written straight into the slot, offset in the header
+        g.slot_array()[:len(rec)] = rec
+        g.publish_inplace(len(rec), first_cycle=2 * r)
+    else:
+        g.publish(rec, first_cycle=2 * r)
+    parts = g.collect()
+    if r == 0:
+        ok &= [len(p) for p in parts] == [3 + step, 4 + step]
+        ok &= set(parts[1]["cycle"].tolist()) == {2, 3} and set(parts[0]["cycle"].tolist()) == {0, 1}
+        ok &= int(parts[1]["cand"][0]) == 100 + step and int(parts[0]["cand"][0]) == step
+    else:
+        ok &= parts is None
+g.close()
+print("SHM_OK" if ok else "SHM_BAD")
+dist.destroy_process_group()
+'''
+
+
+def test_shm_record_gather_world_size_2_gloo(tmp_path):
+    """The N > 1 record gather of bench.py's e2e loop (shared-memory segments + a gloo barrier), two CPU processes."""
+    script = tmp_path / "w.py"
+    script.write_text(_SHM_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHM_OK" in outs[0] and "SHM_OK" in outs[1], outs
+
+
 def test_gather_records_single_process():
     rec = np.zeros(3, L.RECORD_DTYPE)
     out = gather_records(rec, 7)
