@@ -75,7 +75,13 @@ typedef struct ft8_cfg {
     int32_t max_codewords;     /* scratch capacity of the stand-alone ft8_llr/ft8_ldpc/ft8_osd/ft8_crc14 ops (0: default 1<<16) */
     int32_t fine_mode;         /* fine sync (receiver.py:140-206): 0 = time scan + tensor-core frequency scan + final transform
                                   (default); 1 = the literal nine-inverse-FFT kernel (A/B reference for the former)            */
-    int32_t reserved[4];
+    /* Receiver(search_freq_range, search_time_range) as index ranges (receiver.py:311-319): coarse frequency bins
+     * f0 in [search_f0_lo, search_f0_hi) (3.125 Hz each; int(Hz / 3.125)) and hop offsets h0 in [search_h0_lo, search_h0_hi)
+     * (40 ms each; int((t + 0.5) * 25)).  All four zero = the reference defaults [100, 3000] Hz -> [32, 960) and
+     * [-2, 3] s -> [-37, 87), which are also the widest ranges the kernels are built for: any sub-range is honoured,
+     * anything wider is FT8_E_BADARG. */
+    int16_t search_f0_lo, search_f0_hi, search_h0_lo, search_h0_hi;
+    int32_t reserved[2];
 } ft8_cfg;
 
 /* One decoded candidate, as Candidate.check_and_package would see it (receiver.py:51-66). 64 bytes. */

@@ -99,8 +99,11 @@ def full_grid(grid):
 
 
 # --------------------------------------------------------------------------- S2 Costas search
-def search(grid, score_min=85, max_cands=200, odd_even=0):
+def search(grid, score_min=85, max_cands=200, odd_even=0, f0_range=None, h0_range=None):
     """Coarse sync over (f0, h0); one candidate per f0 bin.  receiver.py:338-367.
+
+    f0_range / h0_range: [lo, hi) index ranges as Receiver derives them from search_freq_range / search_time_range
+    (receiver.py:232, 319); None = the defaults [32, 960) and [-37, 87).
 
     Scores only the middle Costas block (rows h0+148+4k); strict '>' from 0;
     keeps score > score_min; stable sort by score descending; first max_cands.
@@ -110,10 +113,12 @@ def search(grid, score_min=85, max_cands=200, odd_even=0):
     cycle_h0 = odd_even * HOPS_PER_CYCLE
     base = 148 + 4 * np.arange(7)                       # receiver.py:322 + :347
     found = []
-    for f0 in range(F0_LO, F0_HI):
+    f_lo, f_hi = f0_range if f0_range is not None else (F0_LO, F0_HI)
+    h_lo, h_hi = h0_range if h0_range is not None else (H0_LO, H0_HI)
+    for f0 in range(f_lo, f_hi):
         strip = g[:, f0:f0 + 14]
         best, best_h0 = 0.0, None
-        for h0 in range(H0_LO, H0_HI):
+        for h0 in range(h_lo, h_hi):
             s = float(np.dot(strip[h0 + cycle_h0 + base, :].ravel(), CSYNC_SEARCH))
             if s > best:
                 best, best_h0 = s, h0

@@ -21,7 +21,9 @@ AP_NAMES = ("NoAP", "CQ", "RR73", "73", "RRR")                          # receiv
 class Cfg(C.Structure):
     _fields_ = [("max_cycles", C.c_int32), ("max_cands", C.c_int32), ("sync_score_min", C.c_float),
                 ("llr_sd_min", C.c_float), ("osd_singleflips", C.c_int32), ("osd_doubleflips", C.c_int32),
-                ("max_codewords", C.c_int32), ("fine_mode", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("max_codewords", C.c_int32), ("fine_mode", C.c_int32),
+                ("search_f0_lo", C.c_int16), ("search_f0_hi", C.c_int16), ("search_h0_lo", C.c_int16), ("search_h0_hi", C.c_int16),
+                ("reserved", C.c_int32 * 2)]
 
 
 class Record(C.Structure):

@@ -276,6 +276,11 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
     if (cfg.osd_singleflips < 0 || cfg.osd_singleflips > OSD_MAX_FLIPS || cfg.osd_doubleflips < 0)
         return fail(nullptr, FT8_E_BADARG, "ft8_create: osd flips out of range");
     if (cfg.max_codewords <= 0) cfg.max_codewords = 1 << 16;
+    if (cfg.search_f0_lo == 0 && cfg.search_f0_hi == 0) { cfg.search_f0_lo = F0_LO; cfg.search_f0_hi = F0_LO + N_F0; }
+    if (cfg.search_h0_lo == 0 && cfg.search_h0_hi == 0) { cfg.search_h0_lo = H0_LO; cfg.search_h0_hi = H0_LO + N_H0; }
+    if (cfg.search_f0_lo < F0_LO || cfg.search_f0_hi > F0_LO + N_F0 || cfg.search_f0_lo >= cfg.search_f0_hi ||
+        cfg.search_h0_lo < H0_LO || cfg.search_h0_hi > H0_LO + N_H0 || cfg.search_h0_lo >= cfg.search_h0_hi)
+        return fail(nullptr, FT8_E_BADARG, "ft8_create: search range outside what the kernels are built for (f0 in [32, 960), h0 in [-37, 87))");
     if (cfg.fine_mode != 0 && cfg.fine_mode != 1) return fail(nullptr, FT8_E_BADARG, "ft8_create: fine_mode must be 0 (tensor-core scan) or 1 (FFT scan)");
     ft8_handle* h = new ft8_handle();
     h->device = device;
@@ -452,10 +457,12 @@ static int launch_sync(ft8_handle* h, const float* d_grid, int grid_rows, int B,
     const int cycle_h0 = odd_even ? 375 : 0;
     const size_t K = h->cfg.max_cands;
     k_sync_scores<<<dim3(SY_HS * (N_F0 / SY_TF), B), SY_NT, SY_SMEM_BYTES, h->stream>>>(
-        d_grid, grid_rows, cycle_h0, h->d_best_score + (size_t)b0 * N_F0 * SY_HS, h->d_best_h0 + (size_t)b0 * N_F0 * SY_HS);
+        d_grid, grid_rows, cycle_h0, h->d_best_score + (size_t)b0 * N_F0 * SY_HS, h->d_best_h0 + (size_t)b0 * N_F0 * SY_HS,
+        h->cfg.search_h0_lo, h->cfg.search_h0_hi);
     CK(cudaGetLastError());
     k_topk<<<B, 960, 0, h->stream>>>(h->d_best_score + (size_t)b0 * N_F0 * SY_HS, h->d_best_h0 + (size_t)b0 * N_F0 * SY_HS, h->cfg.sync_score_min,
-                                     h->cfg.max_cands, h->d_f0 + b0 * K, h->d_h0 + b0 * K, h->d_score + b0 * K, h->d_ncand + b0);
+                                     h->cfg.max_cands, h->d_f0 + b0 * K, h->d_h0 + b0 * K, h->d_score + b0 * K, h->d_ncand + b0,
+                                     h->cfg.search_f0_lo, h->cfg.search_f0_hi);
     CK(cudaGetLastError());
     return FT8_OK;
 }
@@ -558,8 +565,17 @@ extern "C" int ft8_spectrogram(ft8_handle* h, const void* audio, int audio_dtype
 extern "C" int ft8_hop_spectrum(ft8_handle* h, const void* audio_buffer, int audio_dtype, float* row_db, int mem) {
     ENTER(h);
     if (!audio_buffer || !row_db) return fail(h, FT8_E_BADARG, "ft8_hop_spectrum: bad argument");
-    const void* da;
-    TRY(stage_audio(h, audio_buffer, audio_dtype, 1, mem, &da));
+    if (audio_dtype != FT8_AUDIO_I16 && audio_dtype != FT8_AUDIO_F32) return fail(h, FT8_E_BADARG, "audio_dtype must be FT8_AUDIO_I16 or FT8_AUDIO_F32");
+    const size_t esz = audio_dtype == FT8_AUDIO_I16 ? 2 : 4;
+    const void* da = audio_buffer;
+    if (mem == FT8_MEM_HOST) {
+        // only the last 3840 samples are read (receiver.py:289): stage those 15 KB at their place in a cycle-sized buffer,
+        // not the whole 720 KB ring, every 40 ms hop
+        TRY(ensure_audio(h, (size_t)CYCLE_SAMPLES * esz));
+        const size_t off = (size_t)(CYCLE_SAMPLES - NFFT_S) * esz;
+        TRY(to_device(h, (char*)h->d_audio + off, (const char*)audio_buffer + off, (size_t)NFFT_S * esz, mem));
+        da = h->d_audio;
+    }
     float* dr = row_db;
     if (mem == FT8_MEM_HOST) { TRY(ensure_arena(h, GRID_COLS * sizeof(float))); dr = (float*)h->arena; }
     // the window over the last 3840 samples of a 180000-sample buffer is row 375 of that buffer's waterfall

@@ -45,7 +45,7 @@ constexpr int SY_SMEM_BYTES = SY_TROWS * (SY_PW + SY_SW) * 4 + 8 * SY_TF * 4;
 
 __global__ void __launch_bounds__(SY_NT)
 k_sync_scores(const float* __restrict__ grid, int grid_rows, int cycle_h0, float* __restrict__ best_score,
-              int16_t* __restrict__ best_h0) {
+              int16_t* __restrict__ best_h0, int h0_lo, int h0_hi) {
     extern __shared__ __align__(16) unsigned char sy_smem_raw[];
     float* P2 = reinterpret_cast<float*>(sy_smem_raw);
     float* S14 = P2 + SY_TROWS * SY_PW;
@@ -154,7 +154,8 @@ k_sync_scores(const float* __restrict__ grid, int grid_rows, int cycle_h0, float
                     sp += p[20 * SY_PW + C5];
                     sp += p[24 * SY_PW + C6];
                     const float sc = fmaf(c6, U[j] - sp, sp) + residue;      // sum(P2)*1 + (sum(S14) - sum(P2)) * fl(-1/6)
-                    if (sc > best) { best = sc; best_h = half * SY_HPER + hh + H0_LO; }
+                    const int habs = half * SY_HPER + hh + H0_LO;             // search_time_range (receiver.py:319): [h0_lo, h0_hi)
+                    if (sc > best && habs >= h0_lo && habs < h0_hi) { best = sc; best_h = habs; }
                     if (i + 4 < 16 && hh + 4 < SY_HPER) U[j] += sf[(hh + 28) * SY_SW] - sf[hh * SY_SW];
                 }
             }
@@ -179,7 +180,7 @@ k_sync_scores(const float* __restrict__ grid, int grid_rows, int cycle_h0, float
 __global__ void __launch_bounds__(960)
 k_topk(const float* __restrict__ best_score, const int16_t* __restrict__ best_h0, float score_min, int max_cands,
        int16_t* __restrict__ cand_f0, int16_t* __restrict__ cand_h0, float* __restrict__ cand_score,
-       int32_t* __restrict__ n_cand) {
+       int32_t* __restrict__ n_cand, int f0_lo, int f0_hi) {
     __shared__ float sc[N_F0];
     __shared__ int wcount[32];
     const int cyc = blockIdx.x, i = threadIdx.x, lane = i & 31, w = i >> 5;
@@ -193,7 +194,7 @@ k_topk(const float* __restrict__ best_score, const int16_t* __restrict__ best_h0
             if (s > mine) { mine = s; mine_h = best_h0[((size_t)cyc * SY_HS + hf) * N_F0 + i]; }
         }
     }
-    const bool valid = (i < N_F0) && (mine > score_min);
+    const bool valid = (i < N_F0) && (mine > score_min) && (F0_LO + i >= f0_lo) && (F0_LO + i < f0_hi);   // search_freq_range
     const uint32_t m = __ballot_sync(0xffffffffu, valid);
     if (lane == 0) wcount[w] = __popc(m);
     __syncthreads();

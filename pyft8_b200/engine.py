@@ -61,7 +61,8 @@ class _SerialisedLib:
 
 class Engine:
     def __init__(self, device=0, max_cycles=1, max_cands=200, sync_score_min=85.0, llr_sd_min=5.0,
-                 osd_singleflips=30, osd_doubleflips=2, fine_mode=0):
+                 osd_singleflips=30, osd_doubleflips=2, fine_mode=0,
+                 search_f0_range=None, search_h0_range=None):
         self._lock = threading.RLock()
         self._lib = _SerialisedLib(L.load(), self._lock)
         cfg = L.Cfg()
@@ -69,6 +70,10 @@ class Engine:
         cfg.max_cycles, cfg.max_cands = int(max_cycles), int(max_cands)
         cfg.sync_score_min, cfg.llr_sd_min = float(sync_score_min), float(llr_sd_min)
         cfg.osd_singleflips, cfg.osd_doubleflips = int(osd_singleflips), int(osd_doubleflips)
+        if search_f0_range is not None:                   # [lo, hi) in 3.125 Hz bins; None = reference default [32, 960)
+            cfg.search_f0_lo, cfg.search_f0_hi = int(search_f0_range[0]), int(search_f0_range[1])
+        if search_h0_range is not None:                   # [lo, hi) in 40 ms hops; None = reference default [-37, 87)
+            cfg.search_h0_lo, cfg.search_h0_hi = int(search_h0_range[0]), int(search_h0_range[1])
         cfg.fine_mode = int(fine_mode)                    # 0: tensor-core frequency scan (default), 1: nine-FFT kernel (A/B)
         self.cfg = cfg
         self._h = C.c_void_p()

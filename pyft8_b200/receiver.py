@@ -201,9 +201,10 @@ class AudioIn:
         self.search_hops_per_cycle = int(T_CYC * SYM_RATE * self.search_hps)
         self.search_hops_per_grid = 2 * self.search_hops_per_cycle
         self.dt = T_CYC / self.search_hops_per_cycle
-        self.search_grid = np.ones((self.search_hops_per_grid, self.search_f0_idx_range[1] + 8 * self.search_bpt), np.float32)
-        if self.search_grid.shape[1] != L.GRID_COLS:
-            raise ValueError("the CUDA path is built for search_freq_range[1] = 3000 Hz (976 grid columns)")
+        if self.search_f0_idx_range[1] + 8 * self.search_bpt > L.GRID_COLS:
+            raise ValueError("the CUDA path is built for search_freq_range[1] <= 3000 Hz (976 grid columns)")
+        # the library always produces the 976 columns of the default range; a narrower range only restricts the search
+        self.search_grid = np.ones((self.search_hops_per_grid, L.GRID_COLS), np.float32)
         self.samples_per_cycle = int(SAMP_RATE * T_CYC)
         self.search_grid_ptr = int(self._tu.grid_time() * self.search_hops_per_grid / (2 * T_CYC))
         self.last_get_cycle_spectrum = 0
@@ -368,12 +369,17 @@ class Receiver:
     def __init__(self, input_device_keywords, on_message, sync_score_min=85, max_cands=200, search_freq_range=[100, 3000],
                  search_time_range=[-2.5 + 0.5, 2.5 + 0.5], verbose=False, engine=None, clock=None, start_thread=False,
                  batch_cycles=1, device=0):
-        if list(search_time_range) != [-2.0, 3.0] or list(search_freq_range) != [100, 3000]:
-            raise ValueError("the CUDA path is built for the reference's default search ranges ([100,3000] Hz, [-2,3] s)")
         self._tu = TimeUtils(clock)
+        # Receiver(search_freq_range, search_time_range) -> index ranges exactly as the reference derives them
+        # (receiver.py:232, 319); the kernels honour any sub-range of the defaults ([100, 3000] Hz, [-2, 3] s)
+        f0_rng = [int(search_freq_range[0] / (SYM_RATE / 2)), int(search_freq_range[1] / (SYM_RATE / 2))]
+        h0_rng = [int((t + 0.5) * 4 * SYM_RATE) for t in search_time_range]
+        if f0_rng[0] < 32 or f0_rng[1] > 960 or h0_rng[0] < -37 or h0_rng[1] > 87 or f0_rng[0] >= f0_rng[1] or h0_rng[0] >= h0_rng[1]:
+            raise ValueError("the CUDA path supports search ranges inside the reference's defaults ([100, 3000] Hz, [-2, 3] s)")
         # sync engine returns every thresholded bin (max_cands=928) so that search() can honour any f-index subset
         self.engine = engine or Engine(device=device, max_cycles=max(1, batch_cycles), max_cands=928,
-                                       sync_score_min=sync_score_min)
+                                       sync_score_min=sync_score_min, search_f0_range=f0_rng, search_h0_range=h0_rng)
+        self._search_ranges = (f0_rng, h0_rng)
         decoders.set_engine(self.engine)
         self._batch_engine = None
         self._device = device
@@ -459,8 +465,8 @@ class Receiver:
         if self._batch_engine is None or self._batch_engine.max_cycles < B:
             if self._batch_engine is not None:
                 self._batch_engine.close()
-            self._batch_engine = Engine(device=self._device, max_cycles=B, max_cands=self.max_cands,
-                                        sync_score_min=self.sync_score_min)
+            self._batch_engine = Engine(device=self._device, max_cycles=B, max_cands=self.max_cands, sync_score_min=self.sync_score_min,
+                                        search_f0_range=self._search_ranges[0], search_h0_range=self._search_ranges[1])
         rec, n = self._batch_engine.decode_cycles(a, odd_even)
         out = [[] for _ in range(B)]
         seen = [set() for _ in range(B)]
@@ -491,8 +497,8 @@ class Receiver:
         if self._batch_engine is None or self._batch_engine.max_cycles < B:
             if self._batch_engine is not None:
                 self._batch_engine.close()
-            self._batch_engine = Engine(device=self._device, max_cycles=B, max_cands=self.max_cands,
-                                        sync_score_min=self.sync_score_min)
+            self._batch_engine = Engine(device=self._device, max_cycles=B, max_cands=self.max_cands, sync_score_min=self.sync_score_min,
+                                        search_f0_range=self._search_ranges[0], search_h0_range=self._search_ranges[1])
         rec, _ = self._batch_engine.decode_cycles(a, odd_even, next_audio=next_audio)
         return format_records(rec, cyclestart_strings)
 

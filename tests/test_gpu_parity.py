@@ -488,3 +488,41 @@ def test_chunked_host_path_equals_device_path():
     st = e.stats()
     assert st["cycles"] == n and st["decoded"] == len(rec_d) and st["emitted"] == int(rec_d["emitted"].sum())
     e.close()
+
+
+def test_search_range_knobs_match_reference_semantics(golden_cycles):
+    """Receiver(search_freq_range, search_time_range) -> ft8_cfg.search_f0_* / search_h0_* (receiver.py:311-319, 341, 345):
+    candidates are sought only for f0 in [lo, hi) and the per-f0 arg-max only over h0 in [lo, hi)."""
+    audio, g = golden_cycles["test_08"]
+    grid = o.spectrogram(audio)
+    for f_rng, h_rng in (((32, 960), (-37, 87)), ((64, 480), (-37, 87)), ((32, 960), (-12, 40)), ((200, 700), (0, 87)), ((959, 960), (-37, -36))):
+        e = Engine(max_cycles=1, max_cands=200, search_f0_range=f_rng, search_h0_range=h_rng)
+        f0, h0, sc, n, _ = e.sync(grid, want_payload=False)
+        res = o.search(grid, 85, 200, f0_range=f_rng, h0_range=h_rng)
+        fo, ho, so, _ = res
+        n = int(n[0])
+        assert n == len(fo), (f_rng, h_rng, n, len(fo))
+        assert np.array_equal(f0[0, :n], fo) and np.array_equal(h0[0, :n], ho), (f_rng, h_rng)
+        if n:
+            assert f0[0, :n].min() >= f_rng[0] and f0[0, :n].max() < f_rng[1]
+            assert h0[0, :n].min() >= h_rng[0] and h0[0, :n].max() < h_rng[1]
+        # whole path with the restricted search: same decode list as the oracle given the same candidate list
+        rec, cnt = e.decode_cycles(audio)
+        ref = o.decode_cycle(audio, 85, 200, cands=res)[0] if len(fo) else []
+        got = [bits91_to_int(r["bits91"]) >> 14 for r in rec[rec["emitted"] == 1]]
+        assert got == [r["bits77"] for r in ref], (f_rng, h_rng)
+        e.close()
+    for bad in (dict(search_f0_range=(10, 960)), dict(search_f0_range=(32, 1000)), dict(search_h0_range=(-40, 87)), dict(search_h0_range=(5, 5))):
+        with pytest.raises(RuntimeError, match="search range"):
+            Engine(max_cycles=1, **bad)
+
+
+def test_hop_spectrum_reads_only_the_last_window(eng, golden_cycles):
+    """AudioIn.get_hop_spectrum (receiver.py:288-293) uses audio_buffer[-3840:] only: garbage before it must not matter."""
+    audio, _ = golden_cycles["test_09"]
+    a = audio.astype(np.float32)
+    want = eng.hop_spectrum(a)
+    b = a.copy()
+    b[:180000 - 3840] = 12345.0
+    assert np.array_equal(eng.hop_spectrum(b), want)
+    assert np.array_equal(eng.hop_spectrum(audio), want)              # int16 ring buffer gives the same row
