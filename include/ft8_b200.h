@@ -179,6 +179,17 @@ int ft8_crc14(ft8_handle* h, const uint32_t* bits91, int N, int32_t* flags, int 
 int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even,
                       ft8_record* rec, int rec_capacity, int32_t* n_rec, int mem);
 
+/* Live form of ft8_decode_cycles (what a running Receiver sees, receiver.py:238, 295-306, 338-367): the handle keeps, per
+ * stream b < B, the reference's 750-row two-cycle waterfall ring and the previous cycle's last 3840 samples.  Each call
+ * decodes the NEXT 15 s of every stream: its rows are written into the half `odd_even` selects (rows of the other half
+ * still hold the previous cycle; a fresh ring is all 1.0 like np.ones), the first hops' windows reach back into the
+ * previous cycle's audio, the search runs with cycle_h0 = 375 * odd_even, and payload rows wrap mod 750 into the other
+ * half -- so a signal that starts before the cycle boundary (h0 < -32) is read from real rows, as in the reference.
+ * Callers alternate odd_even 0, 1, 0, ... per stream position; ft8_live_reset forgets all streams' history. */
+int ft8_decode_cycles_live(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even,
+                           ft8_record* rec, int rec_capacity, int32_t* n_rec, int mem);
+int ft8_live_reset(ft8_handle* h);
+
 /* Optional double buffering for callers that stream batches from host memory: starts the host->device copy of the NEXT
  * batch on a second stream and returns at once.  The host buffer must stay valid and UNCHANGED until the copy has been
  * consumed or dropped; pinned memory is needed for the copy to be asynchronous.  A pending prefetch is consumed only by

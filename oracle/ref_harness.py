@@ -156,6 +156,52 @@ def decode_cycle(audio_i16, dump=False, t0=30.0 * 1000000, clear_hashes=True, wo
         os.chdir(cwd)
 
 
+def decode_two_cycles(audio_a, audio_b, t0=30.0 * 1000000, workdir=None):
+    """Two CONSECUTIVE cycles through one unmodified Receiver, the way a live receiver sees them (receiver.py:295-306,
+    338-367): A fills ring rows 1..375 and is searched / decoded as the even cycle at its end; B's hops go on into rows
+    376..749, 0 -- its first windows reach back into A's last samples and its early candidates' payload rows wrap into A's
+    half -- and it is searched / decoded as the odd cycle.  Returns [messages of A, messages of B] (lists of dicts)."""
+    rx, dec, tx, db, tu = load_reference()
+    clock = tu.time_utils._clock
+    db.call_hashes.clear()
+    cwd = os.getcwd()
+    if workdir:
+        os.chdir(workdir)
+    try:
+        clock.now = t0
+        out = []
+        msgs = []
+        r = rx.Receiver("", msgs.append)
+        ai = r.audio_in
+        assert ai.search_grid_ptr == 0
+        for half, audio in enumerate((audio_a, audio_b)):
+            audio = np.asarray(audio, dtype=np.int16)
+            base = t0 + 15.0 * half
+            for k in range(375):
+                clock.now = base + (k + 1) * 0.04 + 1e-6
+                ai._callback(audio[480 * k:480 * (k + 1)].tobytes(), 480, None, None)
+            clock.now = base + 15.0
+            cs = tu.time_utils.cyclestart_string(base)
+            cands = r.search(cs, half, range(ai.search_f0_idx_range[0], ai.search_f0_idx_range[1]))
+            n0 = len(msgs)
+            dup = set()
+            for rnd in range(9):
+                todo = [c for c in cands if not c.decode_result]
+                if not todo:
+                    break
+                todo.sort(key=lambda c: c.llr_sd, reverse=True)
+                for c in todo:
+                    c.decode(100)
+                    if c.decode_result is not None and c.decode_result != "stop":
+                        c.check_and_package(dup)
+            out.append(dict(messages=msgs[n0:], n_cands=len(cands),
+                            cand_f0=np.array([c.origin["f0_idx"] for c in cands], np.int32),
+                            cand_h0=np.array([c.origin["h0_idx"] for c in cands], np.int32)))
+        return out
+    finally:
+        os.chdir(cwd)
+
+
 def read_wav_i16(path):
     import wave
     w = wave.open(path, "rb")

@@ -11,8 +11,12 @@ several audio threads: the ring positions and the close-of-cycle decision are gu
 
 What is kept from the reference surface: `on_message(dict)` with the keys of `check_and_package` (receiver.py:61-64)
 plus 'receiver'; `set_band(r, band)`; per-receiver waterfall rows on request (`waterfall(r)`, the 376 x 976 dB grid the
-GUI reads, receiver.py:272-278).  What differs, stated: messages of a cycle are emitted when that cycle has been
-decoded as a whole, not progressively during it.
+GUI reads, receiver.py:272-278); and the live waterfall semantics: each receiver's 750-row two-cycle ring lives on the
+device (`live_ring=True`, ft8_decode_cycles_live), so the first hops of a cycle see the previous cycle's audio and early
+candidates (h0 < -32) read the previous cycle's rows, exactly like a running reference Receiver (receiver.py:295-306,
+360).  What differs, stated: a cycle is searched and decoded when its 15 s are complete (the reference starts searching
+10.4 s into the cycle and decodes candidates as their payload region fills, receiver.py:389-407); the messages are the
+same and come out in the same order, up to 4.6 s later, and "ran out of decoding time" cannot happen.
 """
 import queue
 import threading
@@ -38,11 +42,13 @@ def _pinned(shape):
 
 class ReceiverBank:
     def __init__(self, n_receivers, on_message=None, bands=None, device=0, engine=None, clock=None, sync_score_min=85,
-                 max_cands=200, columnar=False, decoder=None):
+                 max_cands=200, columnar=False, decoder=None, live_ring=True):
         self.n = int(n_receivers)
         self.on_message = on_message
         self.bands = list(bands) if bands is not None else [None] * self.n
         self.columnar = columnar
+        self.live_ring = live_ring    # True: every receiver keeps the reference's two-cycle waterfall ring on the device
+                                      # (ft8_decode_cycles_live); False: each cycle decoded in isolation
         self._tu = TimeUtils(clock)
         self._decoder = decoder       # test seam: callable(audio[R,180000], next_audio) -> record array
         self.engine = engine
@@ -149,7 +155,11 @@ class ReceiverBank:
                     rec = self._decoder(audio)
                 else:
                     with self._eng_lock:
-                        rec, _ = self.engine.decode_cycles(audio, odd_even)
+                        if self.live_ring:
+                            # ring half = cycle number parity (strictly alternating); `odd_even` from the clock is only the label
+                            rec, _ = self.engine.decode_cycles_live(audio, no & 1)
+                        else:
+                            rec, _ = self.engine.decode_cycles(audio, odd_even)
                 with self._cv:                            # audio consumed: the feeder may reuse this half
                     self._busy.discard(half)
                     self._cv.notify_all()

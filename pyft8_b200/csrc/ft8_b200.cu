@@ -55,6 +55,8 @@ struct ft8_handle {
     const void* pf_host = nullptr; int pf_B = 0, pf_dtype = -1;
     cudaEvent_t pf_ev = nullptr;
     float* d_grid = nullptr;
+    // live mode (ft8_decode_cycles_live): the reference's two-cycle waterfall ring per stream + the previous cycle's last window
+    float* d_ring = nullptr; void* d_tail = nullptr; int tail_dtype = -1; bool tail_valid = false;
     float2* d_Y = nullptr; size_t y_cycles = 0;
     float2* d_spec = nullptr;
     float* d_best_score = nullptr; int16_t* d_best_h0 = nullptr;
@@ -392,7 +394,7 @@ extern "C" void ft8_destroy(ft8_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_TS, h->d_TF, h->d_TC, h->d_T256, h->d_W96000T, h->d_hann, h->d_W1920, h->d_W3840, h->d_W3200, h->d_W375, h->d_W256, h->d_W96000, h->d_W192000, h->d_W32,
-                    h->d_pulse, h->d_bmat, h->d_w6400, h->d_zwin, h->d_tso, h->d_ff, h->d_audio, h->d_grid, h->d_Y, h->d_spec, h->d_best_score, h->d_best_h0, h->d_f0, h->d_h0, h->d_score,
+                    h->d_pulse, h->d_ring, h->d_tail, h->d_bmat, h->d_w6400, h->d_zwin, h->d_tso, h->d_ff, h->d_audio, h->d_grid, h->d_Y, h->d_spec, h->d_best_score, h->d_best_h0, h->d_f0, h->d_h0, h->d_score,
                     h->d_ncand, h->d_cycle_of, h->d_status, h->d_llr_grid, h->d_grid_sd, h->d_grid_snr, h->d_llr_fine, h->d_fine,
                     h->d_saved, h->d_saved_n, h->d_saved_ap, h->d_bits, h->d_ripass, h->d_rap, h->d_rmethod, h->d_rnits,
                     h->d_osd_found, h->d_osd_bits, h->d_list_fine, h->d_list_osd, h->d_counts, h->d_stats, h->d_rec, h->d_rec_n, h->d_rec_base, h->arena};
@@ -439,15 +441,18 @@ static CandState cand_state(ft8_handle* h) {
 }
 
 static int launch_spectrogram(ft8_handle* h, const void* d_audio, int dtype, int B, float* d_grid, int row_lo = 1,
-                              int row_hi = 375, int out_rows = GRID_ROWS, int out_row0 = 0, int fill_row0 = 1) {
+                              int row_hi = 375, int out_rows = GRID_ROWS, int out_row0 = 0, int fill_row0 = 1,
+                              const void* d_prev_tail = nullptr, int out_wrap = 0) {
     dim3 grid((row_hi - row_lo + SP_ROWS) / SP_ROWS, B);
     const int smem = SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2);
     if (dtype == FT8_AUDIO_I16)
         k_spectrogram<int16_t><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const int16_t*)d_audio, d_grid, h->d_hann, h->d_TS,
-                                                                          h->d_W3840, row_lo, row_hi, out_rows, out_row0, fill_row0);
+                                                                          h->d_W3840, row_lo, row_hi, out_rows, out_row0, fill_row0,
+                                                                          (const int16_t*)d_prev_tail, out_wrap);
     else
         k_spectrogram<float><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const float*)d_audio, d_grid, h->d_hann, h->d_TS,
-                                                                        h->d_W3840, row_lo, row_hi, out_rows, out_row0, fill_row0);
+                                                                        h->d_W3840, row_lo, row_hi, out_rows, out_row0, fill_row0,
+                                                                        (const float*)d_prev_tail, out_wrap);
     CK(cudaGetLastError());
     return FT8_OK;
 }
@@ -956,18 +961,48 @@ extern "C" int ft8_prefetch_audio(ft8_handle* h, const void* audio_host, int aud
     return FT8_OK;
 }
 
+// the previous cycle's last 3840 samples per stream, kept for the next live call (D2D strided copy on the handle's stream)
+static int save_tails(ft8_handle* h, const void* d_audio, int dtype, int B) {
+    const size_t esz = dtype == FT8_AUDIO_I16 ? 2 : 4;
+    CK(cudaMemcpy2DAsync(h->d_tail, (size_t)NFFT_S * esz, (const char*)d_audio + (size_t)(CYCLE_SAMPLES - NFFT_S) * esz,
+                         (size_t)CYCLE_SAMPLES * esz, (size_t)NFFT_S * esz, (size_t)B, cudaMemcpyDeviceToDevice, h->stream));
+    h->tail_dtype = dtype; h->tail_valid = true;
+    return FT8_OK;
+}
+
+__global__ void k_fill(float* p, size_t n, float v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even, ft8_record* rec,
-                              int rec_capacity, int32_t* n_rec, int mem, const void* next_audio_host, bool consume_pf) {
+                              int rec_capacity, int32_t* n_rec, int mem, const void* next_audio_host, bool consume_pf,
+                              bool live = false) {
     ENTER(h);
     if (!audio || !rec || !n_rec || B <= 0 || rec_capacity < 0) return fail(h, FT8_E_BADARG, "ft8_decode_cycles: bad argument");
     if ((size_t)B > h->cap_cycles) return fail(h, FT8_E_CAPACITY, "ft8_decode_cycles: B exceeds cfg.max_cycles");
     const int K = h->cfg.max_cands, N = B * K;
-    // every cycle of the batch is decoded in isolation on its own 376-row waterfall: the search always runs
-    // with cycle_h0 = 0; odd_even only labels the records on the host side (their_tx_cycle, receiver.py:62)
-    (void)odd_even;
-    const int cycle_h0 = 0;
+    // Isolated mode (default): every cycle is decoded on its own 376-row waterfall, the search runs with
+    // cycle_h0 = 0 and odd_even only labels the records on the host side (their_tx_cycle, receiver.py:62).
+    // Live mode: stream b keeps the reference's 750-row two-cycle ring (receiver.py:238, 295-306); this call's rows go to the
+    // half odd_even selects, rows of the other half still hold the previous cycle, and the first hops' windows reach back into
+    // the previous cycle's last samples -- so candidates with h0 < -32 read real rows, exactly as a live Receiver does.
     if (audio_dtype != FT8_AUDIO_I16 && audio_dtype != FT8_AUDIO_F32) return fail(h, FT8_E_BADARG, "audio_dtype must be FT8_AUDIO_I16 or FT8_AUDIO_F32");
     const size_t esz = audio_dtype == FT8_AUDIO_I16 ? 2 : 4;
+    const int cycle_h0 = live ? (odd_even ? 375 : 0) : 0;
+    const int grows = live ? LIVE_ROWS : GRID_ROWS;
+    float* gbase = h->d_grid;
+    const void* tail = nullptr;
+    if (live) {
+        if (!h->d_ring) {
+            const size_t n = h->cap_cycles * (size_t)LIVE_ROWS * GRID_COLS;
+            CK(dmalloc(&h->d_ring, n));
+            k_fill<<<h->n_sm * 8, 256, 0, h->stream>>>(h->d_ring, n, 1.0f);           // np.ones (receiver.py:238)
+            CK(cudaGetLastError());
+            CK(cudaMalloc(&h->d_tail, h->cap_cycles * (size_t)NFFT_S * 4));
+        }
+        gbase = h->d_ring;
+        if (h->tail_valid && h->tail_dtype == audio_dtype) tail = h->d_tail;
+    }
     const void* da = audio;
     // A pending prefetch is consumed only by the streaming entry (consume_pf), whose caller named this very buffer as the
     // next batch and so promises it has not been rewritten since; every other call drops it -- after waiting for its copy,
@@ -1016,8 +1051,12 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
             if (nb <= 0) continue;
             const char* a = (const char*)h->d_audio + (size_t)b0 * CYCLE_SAMPLES * esz;
             CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
-            TRY(launch_spectrogram(h, a, audio_dtype, nb, h->d_grid + (size_t)b0 * GRID_ROWS * GRID_COLS)); ++launches;
-            TRY(launch_sync(h, h->d_grid + (size_t)b0 * GRID_ROWS * GRID_COLS, GRID_ROWS, nb, 0, b0)); launches += 2;
+            float* gc = gbase + (size_t)b0 * grows * GRID_COLS;
+            const void* tc = tail ? (const char*)tail + (size_t)b0 * NFFT_S * esz : nullptr;
+            if (live) TRY(launch_spectrogram(h, a, audio_dtype, nb, gc, 1, 375, LIVE_ROWS, -cycle_h0, 0, tc, 1));
+            else TRY(launch_spectrogram(h, a, audio_dtype, nb, gc));
+            ++launches;
+            TRY(launch_sync(h, gc, grows, nb, live ? odd_even : 0, b0)); launches += 2;
             TRY(launch_cycle_spectrum(h, a, audio_dtype, nb, h->d_spec + (size_t)b0 * FINE_SPEC_STRIDE, FINE_SPEC_STRIDE, FINE_SPEC_STRIDE - 1));
             launches += 2 * ((nb + (int)h->y_cycles - 1) / (int)h->y_cycles);
         }
@@ -1027,10 +1066,12 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
     } else {
         if (mem == FT8_MEM_HOST) TRY(to_device(h, h->d_audio, audio, (size_t)B * CYCLE_SAMPLES * esz, mem));
         // S1
-        TRY(launch_spectrogram(h, da, audio_dtype, B, h->d_grid)); ++launches;
+        if (live) TRY(launch_spectrogram(h, da, audio_dtype, B, gbase, 1, 375, LIVE_ROWS, -cycle_h0, 0, tail, 1));
+        else TRY(launch_spectrogram(h, da, audio_dtype, B, gbase));
+        ++launches;
         CK(cudaEventRecord(h->ev[1], h->stream));
         // S2
-        TRY(launch_sync(h, h->d_grid, GRID_ROWS, B, 0)); launches += 2;
+        TRY(launch_sync(h, gbase, grows, B, live ? odd_even : 0)); launches += 2;
         CK(cudaEventRecord(h->ev[2], h->stream));
         // F1 (independent of S1/S2; same stream)
         TRY(launch_cycle_spectrum(h, da, audio_dtype, B, h->d_spec, FINE_SPEC_STRIDE, FINE_SPEC_STRIDE - 1));
@@ -1038,10 +1079,11 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
         CK(cudaEventRecord(h->ev[3], h->stream));
     }
     if (next_audio_host && !prefetched) TRY(ft8_prefetch_audio(h, next_audio_host, audio_dtype, B));
+    if (live) TRY(save_tails(h, mem == FT8_MEM_HOST ? h->d_audio : da, audio_dtype, B));      // after S1 / F1 have read this audio
     CandState cs = cand_state(h);
     // ipass 0
     k_pass0<<<persistent_blocks(h, 8), WARPS_PER_CTA * 32, sizeof(PassSmem), h->stream>>>(
-        cs, N, h->d_grid, GRID_ROWS, cycle_h0, h->cfg.llr_sd_min, nullptr, 0, h->d_list_fine, h->d_counts + 0, h->d_counts + 6, h->d_stats);
+        cs, N, gbase, grows, cycle_h0, h->cfg.llr_sd_min, nullptr, 0, h->d_list_fine, h->d_counts + 0, h->d_counts + 6, h->d_stats);
     CK(cudaGetLastError()); ++launches;
     CK(cudaEventRecord(h->ev[4], h->stream));
     // ipass 1
@@ -1099,6 +1141,23 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
 extern "C" int ft8_decode_cycles(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even, ft8_record* rec,
                                  int rec_capacity, int32_t* n_rec, int mem) {
     return decode_cycles_core(h, audio, audio_dtype, B, odd_even, rec, rec_capacity, n_rec, mem, nullptr, false);
+}
+
+extern "C" int ft8_decode_cycles_live(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even, ft8_record* rec,
+                                      int rec_capacity, int32_t* n_rec, int mem) {
+    if (odd_even != 0 && odd_even != 1) return fail(h, FT8_E_BADARG, "ft8_decode_cycles_live: odd_even must be 0 or 1");
+    return decode_cycles_core(h, audio, audio_dtype, B, odd_even, rec, rec_capacity, n_rec, mem, nullptr, false, true);
+}
+
+extern "C" int ft8_live_reset(ft8_handle* h) {
+    ENTER(h);
+    if (h->d_ring) {
+        k_fill<<<h->n_sm * 8, 256, 0, h->stream>>>(h->d_ring, h->cap_cycles * (size_t)LIVE_ROWS * GRID_COLS, 1.0f);
+        CK(cudaGetLastError());
+    }
+    h->tail_valid = false;
+    CK(cudaStreamSynchronize(h->stream));
+    return FT8_OK;
 }
 
 extern "C" int ft8_decode_cycles_stream(ft8_handle* h, const void* audio, int audio_dtype, int B, int odd_even, ft8_record* rec,

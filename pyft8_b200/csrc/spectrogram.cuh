@@ -41,7 +41,7 @@ template <typename T>
 __global__ void __launch_bounds__(SP_ROWS* SP_NT, SP_MIN_BLOCKS)
 k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float* __restrict__ hann,
               const float2* __restrict__ TS, const float2* __restrict__ W3840, int row_lo, int row_hi, int out_rows,
-              int out_row0, int fill_row0) {
+              int out_row0, int fill_row0, const T* __restrict__ prev_tail = nullptr, int out_wrap = 0) {
     extern __shared__ float2 sp_smem[];
     const int cyc = blockIdx.y;
     const int g = threadIdx.x / SP_NT, lt = threadIdx.x % SP_NT;
@@ -49,6 +49,9 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
     const bool live = h <= row_hi;
     float2* buf = sp_smem + g * SP_BUF_LEN * SP_BUFS;
     const T* x = audio + (size_t)cyc * CYCLE_SAMPLES;
+    // live ring (receiver.py:295-306): the windows of the first hops of a cycle reach back into the previous cycle's audio;
+    // prev_tail holds its last 3840 samples per stream (nullptr: isolated cycle, samples before the start read as 0)
+    const T* xp = prev_tail ? prev_tail + (size_t)cyc * NFFT_S : nullptr;
     float* out = grid + (size_t)cyc * out_rows * GRID_COLS;
     if (blockIdx.x == 0 && fill_row0) {
         for (int k = threadIdx.x; k < GRID_COLS; k += blockDim.x) out[k] = 1.0f;
@@ -67,6 +70,10 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
             if (live && si >= 0) {                      // si is even: the pair never straddles the cycle start
                 const float2 w = __ldg(reinterpret_cast<const float2*>(hann + 2 * n));
                 const float2 v = load_sample_pair(x, si);
+                z = cmul_elem(v, w);
+            } else if (live && xp) {                    // si in [-3840, 0): previous cycle's tail
+                const float2 w = __ldg(reinterpret_cast<const float2*>(hann + 2 * n));
+                const float2 v = load_sample_pair(xp, NFFT_S + si);
                 z = cmul_elem(v, w);
             }
             a[j] = z;
@@ -119,7 +126,9 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
 
     // untangle the real transform for bins 0..975 and write dB
     if (live) {
-        float* row = out + (size_t)(h - out_row0) * GRID_COLS;
+        int ri = h - out_row0;
+        if (out_wrap) ri %= out_rows;                   // 750-row ring: row 375 of the odd cycle is ring row 0
+        float* row = out + (size_t)ri * GRID_COLS;
         for (int k = lt; k < GRID_COLS; k += SP_NT) {
             const int km = (k == 0) ? 0 : 1920 - k;
             const float2 zk = buf[k + k / 120];                     // padded layout

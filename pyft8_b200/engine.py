@@ -244,6 +244,22 @@ class Engine:
             self._pf_ref = nx                              # keeps the host buffer alive until its copy is consumed or dropped
         return rec[:int(n[:B].sum())], n[:B]
 
+    def decode_cycles_live(self, audio, odd_even, rec=None, n=None):
+        """Next 15 s of B live streams (row b = stream b): like decode_cycles, but against the handle's per-stream two-cycle
+        waterfall ring and previous-cycle tail (ft8_decode_cycles_live) -- what a running reference Receiver decodes.
+        Alternate odd_even 0, 1, 0, ... call after call; live_reset() forgets the history."""
+        a, dt = self._audio(audio)
+        B = a.shape[0]
+        if rec is None:
+            rec = np.zeros(B * self.max_cands, L.RECORD_DTYPE)
+        if n is None:
+            n = np.zeros(B, np.int32)
+        self._check(self._lib.ft8_decode_cycles_live(self._h, _ptr(a), dt, B, int(odd_even), _ptr(rec), len(rec), _ptr(n), L.MEM_HOST))
+        return rec[:int(n[:B].sum())], n[:B]
+
+    def live_reset(self):
+        self._check(self._lib.ft8_live_reset(self._h))
+
     def prefetch(self, audio):
         """Start copying the NEXT batch (host array, ideally pinned) while the current one is being decoded; the following
         decode_cycles(audio) with the same array consumes the copy (ft8_prefetch_audio)."""

@@ -4,6 +4,7 @@ import pytest
 
 from conftest import load_golden
 from pyft8_b200 import synth
+from pyft8_b200.engine import Engine
 
 pytestmark = pytest.mark.gpu
 
@@ -162,3 +163,82 @@ def test_unconsumed_prefetch_is_dropped():
     assert got[0].tobytes() == want_b[0].tobytes() and np.array_equal(got[1], want_b[1])
     assert want_a[0].tobytes() != want_b[0].tobytes()
     eng.close()
+
+
+def _live_messages(rec, n):
+    """records of one live call (B = 1) -> list of (text, notes, tsec, fHz, snr) of the emitted messages, emission order;
+    hash history is NOT cleared here (the reference keeps it across consecutive cycles)."""
+    from pyft8_b200 import messages
+    from pyft8_b200.receiver import record_to_message
+    out = []
+    seen = set()
+    for r, txt in zip(rec, messages.unpack_words(rec["bits91"])):
+        if txt is None:
+            continue
+        t = " ".join(txt)
+        if t in seen:
+            continue
+        seen.add(t)
+        m = record_to_message(r, msg=txt)
+        out.append((t, m["decode_notes"], m["tsec"], m["fHz"], int(m["their_snr"])))
+    return out
+
+
+@pytest.mark.parametrize("pair", ["wav", "syn"])
+def test_live_ring_two_consecutive_cycles_equal_reference(pair, golden_cycles):
+    """Two consecutive cycles through ft8_decode_cycles_live (per-stream 750-row ring + previous-cycle tail on the device) equal
+    the UNMODIFIED reference Receiver fed the same 30 s hop by hop (oracle/ref_harness.decode_two_cycles): the second cycle's
+    first windows reach into the first cycle's audio and its early candidates (h0 < -32) read the first cycle's rows."""
+    import make_golden_live as mgl
+    from pyft8_b200 import messages
+    g = load_golden("live_pairs.npz")
+    if pair == "wav":
+        a, b = golden_cycles["test_08"][0], golden_cycles["test_09"][0]
+    else:
+        s = mgl.synth_stream(int(g["syn_seed"]))
+        a, b = s[:180000], s[180000:]
+    eng = Engine(max_cycles=1)
+    messages.call_hashes.clear()
+    got = []
+    for half, x in enumerate((a, b)):
+        rec, n = eng.decode_cycles_live(x, half)
+        got.append(_live_messages(rec, n))
+    for i in range(2):
+        want_txt = list(g[f"{pair}_text_{i}"])
+        assert [m[0] for m in got[i]] == want_txt, (pair, i)
+        assert [m[1] for m in got[i]] == list(g[f"{pair}_notes_{i}"]), (pair, i)
+        np.testing.assert_allclose([m[2] for m in got[i]], g[f"{pair}_tsec_{i}"], atol=0.005 + 1e-9)
+        np.testing.assert_allclose([m[3] for m in got[i]], g[f"{pair}_fhz_{i}"], atol=0.5 + 1e-9)
+        assert np.all(np.abs(np.array([m[4] for m in got[i]]) - g[f"{pair}_snr_{i}"]) <= 1)
+    # the ring matters: decoding the second cycle in isolation gives a different candidate list for the early signals
+    if pair == "syn":
+        assert int((g["syn_cand_h0_1"] < -32).sum()) > 0
+    # a reset stream behaves like a fresh Receiver again
+    eng.live_reset()
+    rec, n = eng.decode_cycles_live(a, 0)
+    messages.call_hashes.clear()
+    assert [m[0] for m in _live_messages(rec, n)] == list(g[f"{pair}_text_0"])
+    eng.close()
+
+
+def test_receiver_bank_live_ring_two_cycles(golden_cycles):
+    """The same two consecutive cycles through ReceiverBank (two receivers fed hop by hop, one of them with the pair swapped)."""
+    from pyft8_b200.bank import ReceiverBank
+    from pyft8_b200 import messages
+    g = load_golden("live_pairs.npz")
+    a, b = golden_cycles["test_08"][0], golden_cycles["test_09"][0]
+    messages.call_hashes.clear()
+    got = []
+    bank = ReceiverBank(2, on_message=got.append, clock=lambda: 1000.0)
+    for x0, x1 in ((a, b), (b, a)):
+        for k in range(0, 180000, 4800):
+            bank.feed(0, x0[k:k + 4800])
+            bank.feed(1, x1[k:k + 4800])
+    res = [bank.results(timeout=120), bank.results(timeout=120)]
+    bank.close()
+    by = {(no, r): [] for no in (0, 1) for r in (0, 1)}
+    for no, msgs in res:
+        for m in msgs:
+            by[(no, m["receiver"])].append(" ".join(m["msg_tuple"]))
+    assert sorted(by[(0, 0)]) == sorted(g["wav_text_0"]) and sorted(by[(1, 0)]) == sorted(g["wav_text_1"])
+    assert len(by[(0, 1)]) >= 15 and len(by[(1, 1)]) >= 15

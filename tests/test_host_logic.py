@@ -318,3 +318,20 @@ def test_receiver_bank_buffers_and_hands_over_whole_cycles():
     with pytest.raises(BufferError):                       # one receiver running two cycles ahead of the others
         bank.feed(1, np.zeros(2 * CYCLE_SAMPLES + 1, np.int16))
     bank.close()
+
+
+def test_wav_round_trip_and_cycle_split(tmp_path):
+    from pyft8_b200 import wav
+    g = load_golden("cycle_test_08.npz")["audio"]
+    rec = np.concatenate([g, g[:50000]])                     # 1 full cycle + a partial one
+    p = str(tmp_path / "two.wav")
+    wav.write_wav(p, rec)
+    a = wav.read_wav(p)
+    assert a.shape == (2, 180000) and a.dtype == np.int16
+    assert np.array_equal(a[0], g) and np.array_equal(a[1, :50000], g[:50000]) and not a[1, 50000:].any()
+    assert np.array_equal(wav.read_wav(p, start_sample=1000)[0, :1000], g[1000:2000])
+    import wave
+    with wave.open(str(tmp_path / "bad.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(8000); w.writeframes(b"\\0\\0" * 10)
+    with pytest.raises(ValueError, match="12 kHz"):
+        wav.read_wav(str(tmp_path / "bad.wav"))
