@@ -380,8 +380,13 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
         h->fine_tmp_items = N;
         CKC(dmalloc(&h->d_zwin, N * FS_WIN)); CKC(dmalloc(&h->d_tso, N)); CKC(dmalloc(&h->d_ff, N));
     }
-    CKC(cudaFuncSetAttribute(k_spectrogram<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2)));
-    CKC(cudaFuncSetAttribute(k_spectrogram<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2)));
+    {
+        const int sp_smem = SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2);
+        CKC(cudaFuncSetAttribute(k_spectrogram<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp_smem));
+        CKC(cudaFuncSetAttribute(k_spectrogram<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp_smem));
+        CKC(cudaFuncSetAttribute(k_spectrogram<int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp_smem));
+        CKC(cudaFuncSetAttribute(k_spectrogram<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp_smem));
+    }
     CKC(cudaFuncSetAttribute(k_sync_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES));
     CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -445,14 +450,13 @@ static int launch_spectrogram(ft8_handle* h, const void* d_audio, int dtype, int
                               const void* d_prev_tail = nullptr, int out_wrap = 0) {
     dim3 grid((row_hi - row_lo + SP_ROWS) / SP_ROWS, B);
     const int smem = SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2);
-    if (dtype == FT8_AUDIO_I16)
-        k_spectrogram<int16_t><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const int16_t*)d_audio, d_grid, h->d_hann, h->d_TS,
-                                                                          h->d_W3840, row_lo, row_hi, out_rows, out_row0, fill_row0,
-                                                                          (const int16_t*)d_prev_tail, out_wrap);
-    else
-        k_spectrogram<float><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const float*)d_audio, d_grid, h->d_hann, h->d_TS,
-                                                                        h->d_W3840, row_lo, row_hi, out_rows, out_row0, fill_row0,
-                                                                        (const float*)d_prev_tail, out_wrap);
+    const bool ring = d_prev_tail != nullptr || out_wrap != 0;
+#define SP_LAUNCH(T, RING)                                                                                                          \
+    k_spectrogram<T, RING><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const T*)d_audio, d_grid, h->d_hann, h->d_TS, h->d_W3840, row_lo, \
+                                                                       row_hi, out_rows, out_row0, fill_row0, (const T*)d_prev_tail, out_wrap)
+    if (dtype == FT8_AUDIO_I16) { if (ring) SP_LAUNCH(int16_t, true); else SP_LAUNCH(int16_t, false); }
+    else { if (ring) SP_LAUNCH(float, true); else SP_LAUNCH(float, false); }
+#undef SP_LAUNCH
     CK(cudaGetLastError());
     return FT8_OK;
 }

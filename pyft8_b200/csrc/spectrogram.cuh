@@ -37,7 +37,9 @@ __device__ __forceinline__ float2 load_sample_pair(const float* a, int i) { retu
 #ifndef SP_MIN_BLOCKS
 #define SP_MIN_BLOCKS 8   // 64 registers -> 8 CTAs (32 warps) per SM; measured best on B200
 #endif
-template <typename T>
+// RING = false: isolated cycles (the batch path; compiled exactly as before the live mode existed -- the extra branch in the
+// 15-operand load loop cost 27 % when it was a run-time test).  RING = true: live mode, see prev_tail / out_wrap.
+template <typename T, bool RING = false>
 __global__ void __launch_bounds__(SP_ROWS* SP_NT, SP_MIN_BLOCKS)
 k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float* __restrict__ hann,
               const float2* __restrict__ TS, const float2* __restrict__ W3840, int row_lo, int row_hi, int out_rows,
@@ -51,7 +53,7 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
     const T* x = audio + (size_t)cyc * CYCLE_SAMPLES;
     // live ring (receiver.py:295-306): the windows of the first hops of a cycle reach back into the previous cycle's audio;
     // prev_tail holds its last 3840 samples per stream (nullptr: isolated cycle, samples before the start read as 0)
-    const T* xp = prev_tail ? prev_tail + (size_t)cyc * NFFT_S : nullptr;
+    const T* xp = (RING && prev_tail) ? prev_tail + (size_t)cyc * NFFT_S : nullptr;
     float* out = grid + (size_t)cyc * out_rows * GRID_COLS;
     if (blockIdx.x == 0 && fill_row0) {
         for (int k = threadIdx.x; k < GRID_COLS; k += blockDim.x) out[k] = 1.0f;
@@ -71,7 +73,7 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
                 const float2 w = __ldg(reinterpret_cast<const float2*>(hann + 2 * n));
                 const float2 v = load_sample_pair(x, si);
                 z = cmul_elem(v, w);
-            } else if (live && xp) {                    // si in [-3840, 0): previous cycle's tail
+            } else if (RING && live && xp) {            // si in [-3840, 0): previous cycle's tail
                 const float2 w = __ldg(reinterpret_cast<const float2*>(hann + 2 * n));
                 const float2 v = load_sample_pair(xp, NFFT_S + si);
                 z = cmul_elem(v, w);
@@ -127,7 +129,7 @@ k_spectrogram(const T* __restrict__ audio, float* __restrict__ grid, const float
     // untangle the real transform for bins 0..975 and write dB
     if (live) {
         int ri = h - out_row0;
-        if (out_wrap) ri %= out_rows;                   // 750-row ring: row 375 of the odd cycle is ring row 0
+        if (RING && out_wrap) ri %= out_rows;                   // 750-row ring: row 375 of the odd cycle is ring row 0
         float* row = out + (size_t)ri * GRID_COLS;
         for (int k = lt; k < GRID_COLS; k += SP_NT) {
             const int km = (k == 0) ? 0 : 1920 - k;
