@@ -373,8 +373,8 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
         CKC(cudaMemcpy(h->d_cycle_of, co.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     CKC(cudaFuncSetAttribute(k_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, FINE_SMEM_BYTES));
-    CKC(cudaFuncSetAttribute(k_fine_tscan, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
-    CKC(cudaFuncSetAttribute(k_fine_final, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    CKC(cudaFuncSetAttribute(k_fine_tscan<FT_NT, FT_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
+    CKC(cudaFuncSetAttribute(k_fine_final<FT_NT, FF_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
     CKC(cudaFuncSetAttribute(k_fscan_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
     if (cfg.fine_mode == 0) {
         h->fine_tmp_items = N;
@@ -516,13 +516,13 @@ static int launch_fine(ft8_handle* h, const float2* spec, int spec_stride, const
     }
     const int nbt = list ? persistent_blocks(h, FT_CTAS) : std::min(persistent_blocks(h, FT_CTAS), n_direct);
     const int nb3 = list ? persistent_blocks(h, FF_CTAS) : std::min(persistent_blocks(h, FF_CTAS), n_direct);
-    k_fine_tscan<<<nbt, FINE_NT, FT_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, h->d_tso, h->d_zwin);
+    k_fine_tscan<FT_NT, FT_CTAS><<<nbt, FT_NT, FT_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, h->d_tso, h->d_zwin);
     CK(cudaGetLastError());
     const int nb1 = list ? h->n_sm : std::min(h->n_sm, (n_direct + FS_CAND - 1) / FS_CAND);
     k_fscan_mma<<<nb1, FS_NT, FS_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_tso, h->d_zwin,
                                                          h->d_bmat, h->d_w6400, h->d_ff);
     CK(cudaGetLastError());
-    k_fine_final<<<nb3, FINE_NT, FF_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, h->d_tso, h->d_ff,
+    k_fine_final<FT_NT, FF_CTAS><<<nb3, FT_NT, FF_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, h->d_tso, h->d_ff,
                                                             fo, llr, sig_grid);
     CK(cudaGetLastError());
     return FT8_OK;
