@@ -41,24 +41,31 @@ ALG_BYTES = {
     "sync": 375 * 976 * 4 + 200 * (16 + 58 * 8 * 4),  # per cycle: grid once + candidates/payloads
     "cycle_spectrum": 360000 + 47415 * 8,           # per cycle: audio once + the bins the fine stage reads
     "pass0_ldpc5": 58 * 8 * 4 + 696 + 24,           # per candidate
-    "fine": 9 * 8000 + 58 * 8 * 4,                  # per fine evaluation (candidate)
+    "fine_tscan": 8000 + 224 * 8,                   # per candidate: the 1000-bin band once + the 224 samples it hands on
+    "fine_fscan_mma": 328 * 8 + 224 * 8,            # per candidate: the 328 edge bins + the 224 samples
+    "fine_final": 8000 + 174 * 4,                   # per candidate: the band once more + the LLRs
     "pass234_ldpc": 696 + 696 + 24,                 # per LDPC call
     "osd": 696 + 64,                                # per OSD call
 }
-STAGES = ["all", "spectrogram", "sync", "cycle_spectrum", "pass0_ldpc5", "fine", "pass234_ldpc", "osd", "collect"]
+# index = `which` of ft8_last_kernel_ms; "fine" (5) is the sum of the three kernels 9..11, listed separately in roofline_stages
+STAGES = ["all", "spectrogram", "sync", "cycle_spectrum", "pass0_ldpc5", "fine", "pass234_ldpc", "osd", "collect",
+          "fine_tscan", "fine_fscan_mma", "fine_final"]
 # kernels of each stage (names as tools/ncu_extract.py shortens them) and the work unit its per-unit figures refer to
 STAGE_KERNELS = {"spectrogram": ["k_spectrogram"], "sync": ["k_sync_scores", "k_topk"], "cycle_spectrum": ["k_cs_cols", "k_cs_rows"],
-                 "pass0_ldpc5": ["k_pass0"], "fine": ["k_fine", "k_fine_tscan", "k_fscan_mma", "k_fine_final"],
+                 "pass0_ldpc5": ["k_pass0"], "fine_tscan": ["k_fine_tscan"], "fine_fscan_mma": ["k_fscan_mma"], "fine_final": ["k_fine_final"],
                  "pass234_ldpc": ["k_pass234"], "osd": ["k_osd_items", "k_osd_resolve"]}
-STAGE_UNIT = {"spectrogram": "cycles", "sync": "cycles", "cycle_spectrum": "cycles", "pass0_ldpc5": "candidates", "fine": "fine_evals",
+STAGE_UNIT = {"spectrogram": "cycles", "sync": "cycles", "cycle_spectrum": "cycles", "pass0_ldpc5": "candidates", "fine_tscan": "fine_evals",
+              "fine_fscan_mma": "fine_evals", "fine_final": "fine_evals",
               "pass234_ldpc": "ldpc_calls", "osd": "osd_calls"}
 # what bounds a stage when the committed capture has no counters for its kernels (stated, frac left null -- never "hbm")
-DECLARED_BOUND = {"pass0_ldpc5": "fp32", "fine": "l1_data_pipe", "pass234_ldpc": "fp32", "osd": "int_alu"}
+DECLARED_BOUND = {"pass0_ldpc5": "issue", "fine_tscan": "l1_data_pipe", "fine_fscan_mma": "tensor", "fine_final": "l1_data_pipe",
+                  "pass234_ldpc": "issue", "osd": "int_alu"}
 HBM_STAGES = ("spectrogram", "sync", "cycle_spectrum")          # the stages the north star holds against the HBM roofline
 # on-chip roofs: name -> (ncu utilisation key in the capture, peak key in profiles/peaks_b200.json, unit)
 ONCHIP = {"l1_data_pipe": ("l1_data_pipe_pct", "l1_wavefronts_per_s_lds64", "wavefronts/s"),
           "fp32": ("fma_pipe_pct", "fma_warp_inst_per_s", "warp-inst/s"),
           "int_alu": ("alu_pipe_pct", "int_alu_warp_inst_per_s", "warp-inst/s"),
+          "issue": ("issue_active_pct", "issue_warp_inst_per_s_peak", "warp-inst/s"),
           "tensor": ("tensor_pipe_pct", "tf32_dense_tflops", "TFLOP/s")}
 
 
@@ -460,13 +467,13 @@ def run_gpu(args, dist, rank, local, world):
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms = np.zeros(9)
+    stage_ms = np.zeros(len(STAGES))
     launches = 0
     stats = None
     e0.record(stream)
     for _ in range(args.steps):
         r, n = eng.decode_cycles_dev(audio.data_ptr(), L.AUDIO_I16, B, rec=rec, n=nrec)
-        stage_ms += [eng.last_kernel_ms(i) for i in range(9)]
+        stage_ms += [eng.last_kernel_ms(i) for i in range(len(STAGES))]
         stats = eng.stats()
         launches += stats["kernel_launches"]
     e1.record(stream)

@@ -126,7 +126,8 @@ int  ft8_synchronize(ft8_handle* h);
 void* ft8_stream(ft8_handle* h);
 /* Milliseconds spent on the device (CUDA events on the handle's stream).  After ft8_decode_cycles: which = 0 whole
  * device section, 1 spectrogram, 2 sync (scores + top-K), 3 cycle spectrum, 4 pass 0 (grid LLR + GOOD91 + LDPC5),
- * 5 fine sync, 6 passes 2-4 (LDPC), 7 passes 5-6 (OSD), 8 record collection.  After a stand-alone ft8_spectrogram /
+ * 5 fine sync, 6 passes 2-4 (LDPC), 7 passes 5-6 (OSD), 8 record collection, 9 / 10 / 11 the three kernels of the fine stage
+ * (time scan, tensor-core frequency scan, final transform; 0 with fine_mode 1).  After a stand-alone ft8_spectrogram /
  * ft8_sync call: 1 / 2 = that kernel.  After ft8_ldpc / ft8_osd: 0 = that kernel. */
 int  ft8_last_kernel_ms(ft8_handle* h, int which, float* ms);
 

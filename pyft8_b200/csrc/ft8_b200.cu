@@ -74,8 +74,9 @@ struct ft8_handle {
     DevStats* h_stats = nullptr;      // pinned
     // generic arena for the stand-alone stage ops
     void* arena = nullptr; size_t arena_bytes = 0;
-    cudaEvent_t ev[12] = {};          // ev[0..8]: stage boundaries of ft8_decode_cycles; ev[10], ev[11]: stand-alone ops
-    float last_ms[9] = {};            // see ft8_last_kernel_ms
+    cudaEvent_t ev[14] = {};          // ev[0..8]: stage boundaries of ft8_decode_cycles; ev[10], ev[11]: stand-alone ops;
+                                      // ev[12], ev[13]: between the three kernels of the fine stage
+    float last_ms[12] = {};           // see ft8_last_kernel_ms
     ft8_stats stats{};
 };
 
@@ -429,7 +430,7 @@ extern "C" int ft8_get_stats(ft8_handle* h, ft8_stats* out) {
     return FT8_OK;
 }
 extern "C" int ft8_last_kernel_ms(ft8_handle* h, int which, float* ms) {
-    if (!h || !ms || which < 0 || which > 8) return FT8_E_BADARG;
+    if (!h || !ms || which < 0 || which > 11) return FT8_E_BADARG;
     *ms = h->last_ms[which];
     return FT8_OK;
 }
@@ -518,10 +519,12 @@ static int launch_fine(ft8_handle* h, const float2* spec, int spec_stride, const
     const int nb3 = list ? persistent_blocks(h, FF_CTAS) : std::min(persistent_blocks(h, FF_CTAS), n_direct);
     k_fine_tscan<FT_NT, FT_CTAS><<<nbt, FT_NT, FT_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, h->d_tso, h->d_zwin);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[12], h->stream));
     const int nb1 = list ? h->n_sm : std::min(h->n_sm, (n_direct + FS_CAND - 1) / FS_CAND);
     k_fscan_mma<<<nb1, FS_NT, FS_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_tso, h->d_zwin,
                                                          h->d_bmat, h->d_w6400, h->d_ff);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[13], h->stream));
     k_fine_final<FT_NT, FF_CTAS><<<nb3, FT_NT, FF_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, h->d_tso, h->d_ff,
                                                             fo, llr, sig_grid);
     CK(cudaGetLastError());
@@ -1132,6 +1135,12 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
     const int64_t emitted = (int64_t)h->h_stats->emitted;
     CK(cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[8]));
     for (int i = 1; i <= 8; ++i) CK(cudaEventElapsedTime(&h->last_ms[i], h->ev[i - 1], h->ev[i]));
+    h->last_ms[9] = h->last_ms[10] = h->last_ms[11] = 0.0f;
+    if (h->cfg.fine_mode == 0) {              // the three kernels of the fine stage: time scan, tensor-core frequency scan, final
+        CK(cudaEventElapsedTime(&h->last_ms[9], h->ev[4], h->ev[12]));
+        CK(cudaEventElapsedTime(&h->last_ms[10], h->ev[12], h->ev[13]));
+        CK(cudaEventElapsedTime(&h->last_ms[11], h->ev[13], h->ev[5]));
+    }
     ft8_stats& s = h->stats;
     memset(&s, 0, sizeof(s));
     s.cycles = B; s.candidates = (int64_t)h->h_stats->candidates; s.stopped_sd = (int64_t)h->h_stats->stopped_sd;

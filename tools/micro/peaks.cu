@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// three-input XOR as one LOP3; volatile so that ptxas cannot fold the chain algebraically
+__device__ __forceinline__ unsigned lop3(unsigned a, unsigned b, unsigned c) { unsigned d; asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 __device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 
 enum { FFMA, FFMA2, LOP3, MIX, MUFU, LDS64, LDS128, STS64 };
@@ -45,15 +47,15 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, int ite
         const unsigned x = __float_as_uint(s) | 0x9e3779b9u, y = x * 3u;
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) b[i] = (b[i] & x) ^ (y | b[(i + 1) & 15]);       // one LOP3 each
+            for (int i = 0; i < 16; ++i) b[i] = lop3(b[i], x, y);       // one three-input LOP3 each, 16 independent chains
         }
     } else if (MODE == MIX) {
         const unsigned x = __float_as_uint(s) | 0x9e3779b9u, y = x * 3u;
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a[i] = fmaf(a[i], m, c); b[i] = (b[i] & x) ^ (y | b[(i + 1) & 7]); }
+            for (int i = 0; i < 8; ++i) { a[i] = fmaf(a[i], m, c); b[i] = lop3(b[i], x, y); }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a[i + 8] = fmaf(a[i + 8], m, c); b[i + 8] = (b[i + 8] & x) ^ (y | b[8 + ((i + 1) & 7)]); }
+            for (int i = 0; i < 8; ++i) { a[i + 8] = fmaf(a[i + 8], m, c); b[i + 8] = lop3(b[i + 8], x, y); }
         }
     } else if (MODE == MUFU) {
         for (int it = 0; it < iters; ++it) {
