@@ -1,22 +1,30 @@
 // osd.cuh -- ordered-statistics decoding (order 0 + single/double flips), one warp per codeword.
 //
-// Restates osd_012 (decoders.py:223-272).  The reference runs Gauss-Jordan on a
-// 91x174 uint8 matrix with row/column permutation lists.  Here the matrix is held COLUMN-major,
-// bit-packed: a column is the 91-bit vector of its entries over the rows (3 x u32), so
-//   * the initial matrix G0 = [I | A^T] needs no build step: column c < 91 is the unit vector
-//     e_c and column 91+i is generator row i (constant table c_osd.col);
-//   * columns are visited in reliability order (|llr| descending, ties by ascending index,
-//     NaN last -- numpy's argsort(-|llr|) made stable); sorted position s lives in
-//     lane s%32, register slot s/32, so all register indices are compile-time;
-//   * a pivot step is: broadcast the column (3 shuffles), pick an unused row with a 1 (any such
-//     row gives the same reduced matrix -- the reduced form for a fixed pivot-column set is
-//     unique up to row order, and every result below is expressed through pivots, not row
-//     numbers), then every lane conditionally XORs the pivot column into its 6 columns;
-//   * T = G[:, :91] are the columns with original index < 91 wherever they sit;
-//     trial word bit c = parity(u & col_c) with u[row of pivot k] = hard[column of pivot k];
-//     flipping u at the row of pivot 90-i adds (row of T) = bit (row) of every col_c.
-// CRC-14 is linear, so each of the 1+S vectors carries its 14-bit syndrome and a trial's CRC test is an XOR;
-// the 91-bit word of a trial is only assembled when that XOR is zero.
+// Restates osd_012 (decoders.py:223-272).  The reference runs Gauss-Jordan on a 91x174 uint8 matrix
+// G0 = [I | A^T] with row/column permutation lists and then multiplies trial vectors by G[:, :91].  Everything it
+// produces is a function of the most-reliable basis (the first 91 linearly independent columns in reliability order) and
+// of the order in which its members were found -- not of which row each pivot used -- so the elimination here is free to
+// pick rows, and it only ever stores the 83 PARITY columns (round 2; the first version carried all 174):
+//   * columns are bit-packed over the 91 rows (3 x u32); parity column j lives in lane j%32, register slot j/32;
+//   * columns are visited in reliability order (|llr| descending, ties by ascending index, NaN last -- numpy's
+//     argsort(-|llr|) made stable);
+//   * a systematic column c whose row c is still free is a unit vector: it joins the basis on row c and nothing has to be
+//     eliminated (no matrix work at all);
+//   * a parity column with a 1 in a free row p joins the basis on row p: every other stored column with a 1 in row p gets
+//     the pivot column (row p cleared) XORed in.  The pivot column itself would become the unit vector e_p and carries no
+//     information any more, so its slot is left untouched and from then on holds M[:, p], the image of the systematic
+//     column p under the accumulated row operations (the in-place inversion trick); `own` maps row p -> that slot;
+//   * a systematic column c whose row is taken is that stored image: if it has a 1 in a free row p' it joins the basis on
+//     p' (same update) and its slot becomes the image of column p', else it is dependent;
+//   * when a parity pivot can choose its row it prefers rows whose systematic column sits late in the reliability order
+//     (position >= 96, where the search has usually ended): that column is then never visited as a stored image, which
+//     cuts the eliminations per call from ~60 to ~43 (measured on noise-like llr, tools in profiles/r02_experiments.md).
+// At the end every basis slot holds the image of one NON-basis systematic column c'; the order-0 word is
+//   bit c  = hard decision of c                      for basis systematic columns,
+//   bit c' = parity(image(c') & u), u[row of pivot k] = hard decision of pivot k's column,
+// and flipping pivot k adds bit (row of k) of every image, plus the unit bit of k's own column when it is systematic.
+// CRC-14 is linear, so each of the 1+S vectors carries its 14-bit syndrome and a trial's CRC test is an XOR; the 91-bit
+// word of a trial is only assembled when that XOR is zero.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,23 +40,52 @@ __constant__ OsdTables c_osd;
 constexpr int OSD_MAX_FLIPS = 91;
 
 struct OsdWarpScratch {
+    uint16_t order[176];             // sorted position -> original column | hard decision << 8
     uint8_t piv_row[96];             // pivot k -> row
-    uint16_t syn[OSD_MAX_FLIPS + 1];      // CRC syndrome of [0] the order-0 word, [1+i] the row of T that flip i adds
+    uint8_t piv_col[96];             // pivot k -> original column
+    uint16_t syn[OSD_MAX_FLIPS + 1]; // CRC syndrome of [0] the order-0 word, [1+i] the vector that flip i adds
 };
 
-// Returns trial index + 1 of the first accepted trial word (0 = none); bits = that word.
-// llr: 174 floats in shared or global memory.
-// CTA-shared copy of the generator columns, word-major [3][176]: after the sort every lane asks for a different column, and
-// a lane-indexed read of __constant__ memory is replayed once per distinct address (up to 32 times per load).
+// CTA-shared copies of the constant tables the lanes index differently (a lane-indexed read of __constant__ memory is
+// replayed once per distinct address): generator columns word-major [3][176], CRC syndrome of each codeword bit.
 constexpr int OSD_COL_PITCH = 176;
-struct OsdCtaTables { uint32_t col[3 * OSD_COL_PITCH]; };
+struct OsdCtaTables { uint32_t col[3 * OSD_COL_PITCH]; uint16_t syn[96]; };
 __device__ __forceinline__ void load_osd_tables(OsdCtaTables& t) {
     for (int i = threadIdx.x; i < 174; i += blockDim.x) {
         t.col[i] = c_osd.col[i][0]; t.col[OSD_COL_PITCH + i] = c_osd.col[i][1]; t.col[2 * OSD_COL_PITCH + i] = c_osd.col[i][2];
     }
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) t.syn[i] = (i < 91) ? c_codec.crc_syn[i] : (uint16_t)0;
 }
 
+// a[w] for a warp-uniform w in 0..2 without branches (the ternary form compiles to a BSSY / BRA / BSYNC diamond)
+__device__ __forceinline__ uint32_t sel3(int w, uint32_t a0, uint32_t a1, uint32_t a2) {
+    uint32_t r;
+    asm("{\n .reg .pred p0, p1;\n setp.eq.s32 p0, %1, 0;\n setp.eq.s32 p1, %1, 1;\n selp.b32 %0, %3, %4, p1;\n selp.b32 %0, %2, %0, p0;\n}"
+        : "=&r"(r) : "r"(w), "r"(a0), "r"(a1), "r"(a2));
+    return r;
+}
+// One elimination step on a lane's three stored columns: slot k gets (x0, x1, x2) XORed in when its word `T` has the pivot
+// bit and it is not the pivot's own slot (j == 32 k + lane); the own slot records the pivot row instead.  Written in PTX so
+// that the XORs stay predicated (the C form becomes nine SELs and nine LOP3s).
+#define OSD_ELIM(T0, T1, T2)                                                                                              \
+    asm("{\n .reg .pred q0, q1, q2, n0, n1, n2;\n .reg .b32 t0, t1, t2, l1, l2;\n"                                      \
+        " add.s32 l1, %16, 32;\n add.s32 l2, %16, 64;\n"                                                                  \
+        " setp.eq.s32 n0, %15, %16;\n setp.eq.s32 n1, %15, l1;\n setp.eq.s32 n2, %15, l2;\n"                              \
+        " and.b32 t0, %18, %12;\n and.b32 t1, %19, %12;\n and.b32 t2, %20, %12;\n"                                        \
+        " setp.ne.and.b32 q0, t0, 0, !n0;\n setp.ne.and.b32 q1, t1, 0, !n1;\n setp.ne.and.b32 q2, t2, 0, !n2;\n"          \
+        " @q0 xor.b32 %0, %0, %13;\n @q0 xor.b32 %1, %1, %14;\n @q0 xor.b32 %2, %2, %21;\n"                               \
+        " @q1 xor.b32 %3, %3, %13;\n @q1 xor.b32 %4, %4, %14;\n @q1 xor.b32 %5, %5, %21;\n"                               \
+        " @q2 xor.b32 %6, %6, %13;\n @q2 xor.b32 %7, %7, %14;\n @q2 xor.b32 %8, %8, %21;\n"                               \
+        " @n0 mov.b32 %9, %17;\n @n1 mov.b32 %10, %17;\n @n2 mov.b32 %11, %17;\n}"                                        \
+        : "+r"(c0[0]), "+r"(c1[0]), "+r"(c2[0]), "+r"(c0[1]), "+r"(c1[1]), "+r"(c2[1]), "+r"(c0[2]), "+r"(c1[2]), "+r"(c2[2]), \
+          "+r"(ownrow[0]), "+r"(ownrow[1]), "+r"(ownrow[2])                                                               \
+        : "r"(pb), "r"(x0), "r"(x1), "r"(j), "r"(lane), "r"(p), "r"(T0), "r"(T1), "r"(T2), "r"(x2))
+
+
+// Returns trial index + 1 of the first accepted trial word (0 = none); bits = that word.
+// llr: 174 floats in shared or global memory.
 __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g, const float* llr, int lane, const LaneSyn& ls, int S, int D, uint32_t* bits) {
+    constexpr uint32_t FULL = 0xffffffffu;
     // ---- 1. reliability order: bitonic sort of 256 64-bit keys (8 per lane, slot e = 32*r + lane), descending.
     //      key = (|llr| bits + 1, or 0 for NaN) << 8 | (255 - index): larger |llr| first, ties by ascending index, NaN after
     //      every number, the 82 padding slots (key 0) last.  Slot e ends up holding the e-th column in reliability order.
@@ -95,96 +132,128 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
             }
         }
     }
-    // ---- 2. load columns in sorted order; hard decisions per sorted position
-    uint32_t c0[6], c1[6], c2[6];
-    uint32_t hard_mask = 0;          // bit r: hard decision of this lane's slot r
-    uint32_t orig[6];
+    // ---- 2. publish the order with the hard decisions; rows whose systematic column comes late (position >= 96)
+    uint32_t L0 = 0, L1 = 0, L2 = 0;
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
         const int sp = lane + 32 * r;
         if (sp < 174) {
             const int c = 255 - (int)(key[r] & 0xFFull);
-            orig[r] = c;
-            c0[r] = g.col[c]; c1[r] = g.col[OSD_COL_PITCH + c]; c2[r] = g.col[2 * OSD_COL_PITCH + c];
-            if (llr[c] > 0.0f) hard_mask |= 1u << r;
-        } else {
-            orig[r] = 255; c0[r] = c1[r] = c2[r] = 0;
+            s.order[sp] = (uint16_t)(c | ((llr[c] > 0.0f) ? 0x100 : 0));
+            if (r >= 3 && c < 91) {
+                const uint32_t b = 1u << (c & 31);
+                if (c < 32) L0 |= b; else if (c < 64) L1 |= b; else L2 |= b;
+            }
         }
     }
-    // ---- 3. Gauss-Jordan over columns in sorted order
+    L0 = __reduce_or_sync(FULL, L0); L1 = __reduce_or_sync(FULL, L1); L2 = __reduce_or_sync(FULL, L2);
+    // ---- 3. the 83 parity columns (slot r of lane l: parity column 32 r + l), eliminated in place
+    uint32_t c0[3], c1[3], c2[3];
+    uint32_t ownrow[3];               // row (= systematic column) whose image the slot holds, 255: not a basis slot
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int j = 32 * r + lane;
+        ownrow[r] = 255;
+        if (j < 83) { c0[r] = g.col[91 + j]; c1[r] = g.col[OSD_COL_PITCH + 91 + j]; c2[r] = g.col[2 * OSD_COL_PITCH + 91 + j]; }
+        else c0[r] = c1[r] = c2[r] = 0u;
+    }
+    uint32_t own0 = 0, own1 = 0, own2 = 0;        // slot holding the image of row lane / 32 + lane / 64 + lane
     uint32_t used0 = 0, used1 = 0, used2 = 0;     // rows already holding a pivot
     uint32_t u0 = 0, u1 = 0, u2 = 0;              // u[row] = hard decision of that row's pivot column
+    uint32_t hs0 = 0, hs1 = 0, hs2 = 0;           // hard decisions of the basis' systematic columns, by column
     int npiv = 0;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        for (int l = 0; l < 32; ++l) {
-            if (npiv >= 91 || r * 32 + l >= 174) break;
-            const uint32_t v0 = __shfl_sync(0xffffffffu, c0[r], l);
-            const uint32_t v1 = __shfl_sync(0xffffffffu, c1[r], l);
-            const uint32_t v2 = __shfl_sync(0xffffffffu, c2[r], l);
-            const uint32_t f0 = v0 & ~used0, f1 = v1 & ~used1, f2 = v2 & ~used2;
-            if ((f0 | f1 | f2) == 0) continue;    // dependent column
-            int p;
-            if (f0) p = __ffs(f0) - 1; else if (f1) p = 32 + __ffs(f1) - 1; else p = 64 + __ffs(f2) - 1;
-            const uint32_t pb = 1u << (p & 31);
-            const int pw = p >> 5;
-            uint32_t m0 = v0, m1 = v1, m2 = v2;   // pivot column with the pivot row cleared
-            if (pw == 0) { m0 &= ~pb; used0 |= pb; } else if (pw == 1) { m1 &= ~pb; used1 |= pb; } else { m2 &= ~pb; used2 |= pb; }
-            const uint32_t hb = __shfl_sync(0xffffffffu, hard_mask >> r, l) & 1u;
-            if (hb) { if (pw == 0) u0 |= pb; else if (pw == 1) u1 |= pb; else u2 |= pb; }
-            if (lane == 0) s.piv_row[npiv] = (uint8_t)p;
-            ++npiv;
-            // A column that is still a unit vector (an untouched systematic column) eliminates nothing: skip the update.
-            if ((m0 | m1 | m2) == 0) continue;
-            // pw is warp-uniform: three copies of the update, each testing a fixed word
-            if (pw == 0) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) if (c0[k] & pb) { c0[k] ^= m0; c1[k] ^= m1; c2[k] ^= m2; }
-            } else if (pw == 1) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) if (c1[k] & pb) { c0[k] ^= m0; c1[k] ^= m1; c2[k] ^= m2; }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) if (c2[k] & pb) { c0[k] ^= m0; c1[k] ^= m1; c2[k] ^= m2; }
+    __syncwarp();
+    uint32_t e_next = s.order[0];
+    for (int sp = 0; sp < 174; ++sp) {
+        const uint32_t e = e_next;
+        e_next = s.order[sp + 1];                 // order[] is padded; the entry after the last one is never used
+        const int c = (int)(e & 0xFFu);
+        const bool hb = (e >> 8) != 0;
+        int j;
+        if (c < 91) {
+            const int w = c >> 5;
+            const uint32_t b = 1u << (c & 31);
+            if ((sel3(w, used0, used1, used2) & b) == 0) {        // untouched unit vector on a free row: nothing to eliminate
+                if (w == 0) { used0 |= b; if (hb) { u0 |= b; hs0 |= b; } }
+                else if (w == 1) { used1 |= b; if (hb) { u1 |= b; hs1 |= b; } }
+                else { used2 |= b; if (hb) { u2 |= b; hs2 |= b; } }
+                if (lane == 0) { s.piv_row[npiv] = (uint8_t)c; s.piv_col[npiv] = (uint8_t)c; }
+                if (++npiv == 91) break;
+                continue;
             }
+            j = (int)__shfl_sync(FULL, sel3(w, own0, own1, own2), c & 31);       // its image lives in a basis slot
+        } else {
+            j = c - 91;
         }
+        const int jl = j & 31, jr = j >> 5;
+        const uint32_t v0 = __shfl_sync(FULL, sel3(jr, c0[0], c0[1], c0[2]), jl);
+        const uint32_t v1 = __shfl_sync(FULL, sel3(jr, c1[0], c1[1], c1[2]), jl);
+        const uint32_t v2 = __shfl_sync(FULL, sel3(jr, c2[0], c2[1], c2[2]), jl);
+        const uint32_t f0 = v0 & ~used0, f1 = v1 & ~used1, f2 = v2 & ~used2;
+        if ((f0 | f1 | f2) == 0) continue;        // dependent column
+        uint32_t g0 = f0 & L0, g1 = f1 & L1, g2 = f2 & L2;
+        if ((g0 | g1 | g2) == 0) { g0 = f0; g1 = f1; g2 = f2; }
+        const int pw = g0 ? 0 : (g1 ? 1 : 2);
+        const uint32_t gw = sel3(pw, g0, g1, g2);
+        const uint32_t pb = gw & (0u - gw);
+        const int pl = 31 - __clz(pb);
+        const int p = 32 * pw + pl;
+        if (lane == 0) { s.piv_row[npiv] = (uint8_t)p; s.piv_col[npiv] = (uint8_t)c; }
+        if (c < 91 && hb) {
+            const uint32_t b = 1u << (c & 31);
+            if (c < 32) hs0 |= b; else if (c < 64) hs1 |= b; else hs2 |= b;
+        }
+        // pw is warp-uniform: three copies of the update, each testing a fixed word
+        uint32_t x0 = v0, x1 = v1, x2 = v2;       // the pivot column with the pivot row cleared
+        if (pw == 0) {
+            used0 |= pb; if (hb) u0 |= pb;
+            if (lane == pl) own0 = (uint32_t)j;
+            x0 &= ~pb;
+            OSD_ELIM(c0[0], c0[1], c0[2]);
+        } else if (pw == 1) {
+            used1 |= pb; if (hb) u1 |= pb;
+            if (lane == pl) own1 = (uint32_t)j;
+            x1 &= ~pb;
+            OSD_ELIM(c1[0], c1[1], c1[2]);
+        } else {
+            used2 |= pb; if (hb) u2 |= pb;
+            if (lane == pl) own2 = (uint32_t)j;
+            x2 &= ~pb;
+            OSD_ELIM(c2[0], c2[1], c2[2]);
+        }
+        if (++npiv == 91) break;
     }
     __syncwarp();
-    // ---- 4. CRC syndromes of the 1+S vectors over the original columns 0..90 (vector 0 = order-0 word, vector 1+i = row
-    //      of T that flip i adds).  Only the 14-bit syndromes are needed to test a trial; the 91-bit words themselves are
-    //      built on demand (osd_word) for the rare trials whose syndrome is zero.
-    //      Each slot first fetches the syndrome contribution of its original column from the lanes' register table.
-    uint32_t slot_syn[6];
+    // ---- 4. CRC syndromes of the 1+S vectors (vector 0 = order-0 word, vector 1+i = what flip i adds).  Only the 14-bit
+    //      syndromes are needed to test a trial; the 91-bit words themselves are built on demand (osd_word) for the rare
+    //      trials whose syndrome is zero.  A slot that is not a basis slot contributes nothing (syndrome 0).
+    uint32_t slot_syn[3];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const uint32_t c = orig[k];
-        const uint32_t a0 = __shfl_sync(0xffffffffu, ls.s0, c & 31);
-        const uint32_t a1 = __shfl_sync(0xffffffffu, ls.s1, c & 31);
-        const uint32_t a2 = __shfl_sync(0xffffffffu, ls.s2, c & 31);
-        slot_syn[k] = (c < 32) ? a0 : ((c < 64) ? a1 : ((c < 91) ? a2 : 0u));
-    }
+    for (int k = 0; k < 3; ++k) slot_syn[k] = (ownrow[k] < 91) ? (uint32_t)g.syn[ownrow[k]] : 0u;
     const int nvec = 1 + S;
-    for (int vi = 0; vi < nvec; ++vi) {
-        uint32_t syn = 0;
-        if (vi == 0) {
+    {
+        uint32_t syn = (((hs0 >> lane) & 1u) ? ls.s0 : 0u) ^ (((hs1 >> lane) & 1u) ? ls.s1 : 0u) ^ (((hs2 >> lane) & 1u) ? ls.s2 : 0u);
 #pragma unroll
-            for (int k = 0; k < 6; ++k)
-                if ((__popc(c0[k] & u0) + __popc(c1[k] & u1) + __popc(c2[k] & u2)) & 1) syn ^= slot_syn[k];
+        for (int k = 0; k < 3; ++k)
+            if ((__popc(c0[k] & u0) + __popc(c1[k] & u1) + __popc(c2[k] & u2)) & 1) syn ^= slot_syn[k];
+        syn = __reduce_xor_sync(FULL, syn);
+        if (lane == 0) s.syn[0] = (uint16_t)syn;
+    }
+    for (int vi = 1; vi < nvec; ++vi) {
+        const int prow = s.piv_row[91 - vi], pcol = s.piv_col[91 - vi];
+        const uint32_t pbit = 1u << (prow & 31);
+        uint32_t syn = (lane == 0) ? (uint32_t)g.syn[pcol < 91 ? pcol : 95] : 0u;       // syn[95] = 0: parity pivots add no unit bit
+        if (prow < 32) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) if (c0[k] & pbit) syn ^= slot_syn[k];
+        } else if (prow < 64) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) if (c1[k] & pbit) syn ^= slot_syn[k];
         } else {
-            const int prow = s.piv_row[90 - (vi - 1)];
-            const uint32_t pbit = 1u << (prow & 31);
-            if (prow < 32) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) if (c0[k] & pbit) syn ^= slot_syn[k];
-            } else if (prow < 64) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) if (c1[k] & pbit) syn ^= slot_syn[k];
-            } else {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) if (c2[k] & pbit) syn ^= slot_syn[k];
-            }
+            for (int k = 0; k < 3; ++k) if (c2[k] & pbit) syn ^= slot_syn[k];
         }
-        syn = __reduce_xor_sync(0xffffffffu, syn);
+        syn = __reduce_xor_sync(FULL, syn);
         if (lane == 0) s.syn[vi] = (uint16_t)syn;
     }
     __syncwarp();
@@ -192,10 +261,11 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
     auto osd_word = [&](int vi, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
         if (vi < 0) return;
         uint32_t x0 = 0, x1 = 0, x2 = 0;
-        const int prow = vi > 0 ? s.piv_row[90 - (vi - 1)] : 0;
+        const int prow = vi > 0 ? s.piv_row[91 - vi] : 0;
+        const int pcol = vi > 0 ? s.piv_col[91 - vi] : 255;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const uint32_t c = orig[k];
+        for (int k = 0; k < 3; ++k) {
+            const int c = ownrow[k];
             if (c < 91) {
                 uint32_t b;
                 if (vi == 0) b = (__popc(c0[k] & u0) + __popc(c1[k] & u1) + __popc(c2[k] & u2)) & 1u;
@@ -203,9 +273,10 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
                 if (b) { const uint32_t bit = 1u << (c & 31); if (c < 32) x0 |= bit; else if (c < 64) x1 |= bit; else x2 |= bit; }
             }
         }
-        w0 ^= __reduce_or_sync(0xffffffffu, x0);
-        w1 ^= __reduce_or_sync(0xffffffffu, x1);
-        w2 ^= __reduce_or_sync(0xffffffffu, x2);
+        x0 = __reduce_or_sync(FULL, x0); x1 = __reduce_or_sync(FULL, x1); x2 = __reduce_or_sync(FULL, x2);
+        if (vi == 0) { x0 |= hs0; x1 |= hs1; x2 |= hs2; }
+        else if (pcol < 91) { const uint32_t bit = 1u << (pcol & 31); if (pcol < 32) x0 |= bit; else if (pcol < 64) x1 |= bit; else x2 |= bit; }
+        w0 ^= x0; w1 ^= x1; w2 ^= x2;
     };
     // ---- 5. enumerate trials in the reference's order; first with payload != 0, CRC ok, valid payload
     //      trial 0: base; 1..S: single flips i = 0..S-1; then pairs (i, j), j < D, j < i, i-major.
@@ -213,6 +284,7 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
     int npair = 0;
     for (int i = 0; i < S; ++i) npair += min(i, D);
     const int ntrial = 1 + nsingle + npair;
+    const int tri = D * (D - 1) / 2;               // pairs of the rows i < D (row i has i of them); every later row has D
     const uint32_t bs = s.syn[0];
     for (int base = 0; base < ntrial; base += 32) {
         const int tr = base + lane;
@@ -223,20 +295,19 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
             else if (tr <= nsingle) fi = tr - 1;
             else {
                 int q = tr - 1 - nsingle;      // q-th pair
-                int i = 0;
-                while (true) { const int cnt = min(i, D); if (q < cnt) break; q -= cnt; ++i; }
-                fi = i; fj = q;
+                if (q >= tri && D > 0) { q -= tri; fi = D + q / D; fj = q - (fi - D) * D; }
+                else { int i = 0; while (q >= i) { q -= i; ++i; } fi = i; fj = q; }
             }
             uint32_t syn = bs;
             if (fi >= 0) syn ^= s.syn[1 + fi];
             if (fj >= 0) syn ^= s.syn[1 + fj];
             pass = (syn == 0);
         }
-        uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+        uint32_t ballot = __ballot_sync(FULL, pass);
         while (ballot) {
             const int src = __ffs(ballot) - 1;
             ballot &= ballot - 1;
-            const int sfi = __shfl_sync(0xffffffffu, fi, src), sfj = __shfl_sync(0xffffffffu, fj, src);
+            const int sfi = __shfl_sync(FULL, fi, src), sfj = __shfl_sync(FULL, fj, src);
             uint32_t w[3] = {0u, 0u, 0u};
             osd_word(0, w[0], w[1], w[2]);
             osd_word(sfi >= 0 ? 1 + sfi : -1, w[0], w[1], w[2]);

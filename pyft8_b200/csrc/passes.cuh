@@ -87,7 +87,18 @@ __device__ __forceinline__ void set_result(const CandState& cs, int slot, const 
 }
 
 // ipass 0.  grid: [B][grid_rows][976].  payload_db (optional): [N][58][8].
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
+// prev[] of the decoder in registers needs ~90 registers: 5 CTAs/SM instead of 8 (measured: 5.80 ms with prev in shared
+// memory at 8 CTAs, 5.02 with the one-reciprocal update, 4.33 with prev in registers at 5 CTAs)
+#ifndef PASS0_PREG
+#define PASS0_PREG true
+#endif
+#ifndef PASS0_MINB
+#define PASS0_MINB 5
+#endif
+#ifndef PASS234_MINB
+#define PASS234_MINB 6
+#endif
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, PASS0_MINB)
 k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows, int cycle_h0, float sd_min,
         float* __restrict__ payload_db, int llr_only, int32_t* __restrict__ list_fine, int32_t* __restrict__ count_fine,
         int32_t* __restrict__ next_slot, DevStats* __restrict__ stats) {
@@ -152,7 +163,7 @@ k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows
                 break;
             }
             int nits, iters = 0;
-            const int st = ldpc_warp(ws, sm.tab, lane, ls, 35, 5, nits, bits, iters);
+            const int st = ldpc_warp<PASS0_PREG>(ws, sm.tab, lane, ls, 35, 5, nits, bits, iters);
             ++n_ldpc; n_iter += iters;
             if (st == 1) {
                 if (lane == 0) set_result(cs, slot, bits, 0, ap, 1 /*LDPC5*/, nits);
@@ -172,7 +183,7 @@ k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows
 }
 
 // ipass 2..4 over list_fine.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, PASS234_MINB)
 k_pass234(CandState cs, const int32_t* __restrict__ list, const int32_t* __restrict__ count, float sd_min,
           int32_t* __restrict__ list_osd, int32_t* __restrict__ count_osd, int32_t* __restrict__ next_item,
           DevStats* __restrict__ stats) {
@@ -221,7 +232,7 @@ k_pass234(CandState cs, const int32_t* __restrict__ list, const int32_t* __restr
             const int ap = p4 ? a - 2 : a;
             apply_ap(ws.llr, llr0, ap, lane);
             int nits, iters = 0;
-            const int st = ldpc_warp(ws, sm.tab, lane, ls, p4 ? 90 : 35, p4 ? 20 : 5, nits, bits, iters);
+            const int st = ldpc_warp<true>(ws, sm.tab, lane, ls, p4 ? 90 : 35, p4 ? 20 : 5, nits, bits, iters);
             ++n_ldpc; n_iter += iters;
             if (st == 1) { if (lane == 0) set_result(cs, slot, bits, p4 ? 4 : 3, ap, p4 ? 2 : 1, nits); done = true; }
             else if (p4 && st >= 2) {                         // FAIL or STALL: reference keeps the llr (receiver.py:128-129)
@@ -340,7 +351,7 @@ k_ldpc_batch(float* __restrict__ llr, int N, int max_ncheck0, int max_iters, int
         __syncwarp();
         uint32_t bits[3];
         int nits, iters = 0;
-        const int st = ldpc_warp(ws, sm.tab, lane, ls, max_ncheck0, max_iters, nits, bits, iters);
+        const int st = ldpc_warp<true>(ws, sm.tab, lane, ls, max_ncheck0, max_iters, nits, bits, iters);
         __syncwarp();
         for (int i = lane; i < 174; i += 32) llr[(size_t)n * 174 + i] = ws.llr[i];
         if (lane == 0) {

@@ -32,6 +32,7 @@ def child(B, reps):
     out = {"lib": os.environ.get("PYFT8_B200_LIB", "default"), "B": B, "records": int(len(rec)),
            "digest": hashlib.sha1(rec.tobytes()).hexdigest()[:12],
            "ms": {k: round(float(v), 3) for k, v in zip(STAGES, np.median(ms, axis=0))}}
+    np.save("/tmp/vb_%s.npy" % os.path.basename(out["lib"]), rec)
     print("VARIANT " + json.dumps(out), flush=True)
 
 
@@ -47,3 +48,16 @@ if __name__ == "__main__":
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", str(B), "5"], env=env, capture_output=True, text=True)
             lines = [l for l in p.stdout.splitlines() if l.startswith("VARIANT ")]
             print(lines[0] if lines else "FAILED %s: %s" % (lib, (p.stderr or p.stdout)[-800:]), flush=True)
+        # field-level difference of every variant's records against the first one's
+        import numpy as np
+        recs = [np.load("/tmp/vb_%s.npy" % os.path.basename(lib)) for lib in sys.argv[1:] if os.path.exists("/tmp/vb_%s.npy" % os.path.basename(lib))]
+        for lib, r in zip(sys.argv[2:], recs[1:]):
+            a = recs[0]
+            if len(a) != len(r):
+                print("DIFF %s: record count %d vs %d" % (lib, len(a), len(r)))
+                continue
+            bad = np.nonzero((a.view(np.uint8).reshape(len(a), -1) != r.view(np.uint8).reshape(len(r), -1)).any(1))[0]
+            fields = {f: int((a[f][bad] != r[f][bad]).reshape(len(bad), -1).any(1).sum()) for f in a.dtype.names}
+            print("DIFF %s: %d records differ; per field %s" % (lib, len(bad), {k: v for k, v in fields.items() if v}))
+            for i in bad[:6]:
+                print("   base", a[i], "\n   this", r[i])
