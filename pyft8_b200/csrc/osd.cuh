@@ -44,7 +44,11 @@ struct OsdWarpScratch {
     uint8_t piv_row[96];             // pivot k -> row
     uint8_t piv_col[96];             // pivot k -> original column
     uint16_t syn[OSD_MAX_FLIPS + 1]; // CRC syndrome of [0] the order-0 word, [1+i] the vector that flip i adds
+    uint16_t ssyn[96];               // CRC syndrome of the systematic column whose image slot j holds (0: not a basis slot)
+    uint32_t colw[3 * 97];           // the stored columns word-major [3][OSD_W_PITCH] (odd pitch: the three words of a slot
+                                     // sit in different banks)
 };
+constexpr int OSD_W_PITCH = 97;
 
 // CTA-shared copies of the constant tables the lanes index differently (a lane-indexed read of __constant__ memory is
 // replayed once per distinct address): generator columns word-major [3][176], CRC syndrome of each codeword bit.
@@ -86,63 +90,104 @@ __device__ __forceinline__ uint32_t sel3(int w, uint32_t a0, uint32_t a1, uint32
 // llr: 174 floats in shared or global memory.
 __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g, const float* llr, int lane, const LaneSyn& ls, int S, int D, uint32_t* bits) {
     constexpr uint32_t FULL = 0xffffffffu;
-    // ---- 1. reliability order: bitonic sort of 256 64-bit keys (8 per lane, slot e = 32*r + lane), descending.
-    //      key = (|llr| bits + 1, or 0 for NaN) << 8 | (255 - index): larger |llr| first, ties by ascending index, NaN after
-    //      every number, the 82 padding slots (key 0) last.  Slot e ends up holding the e-th column in reliability order.
-    unsigned long long key[8];
+    // ---- 1. reliability order.  Fast path: bitonic sort of 256 32-bit keys (8 per lane, slot e = 32*r + lane), descending,
+    //      key = code(|llr|) << 8 | (255 - index) with a monotone 24-bit code (zero, or 5 exponent bits for [2^-26, 2^5)
+    //      and the top 19 mantissa bits); padding slots are 0.  The order by (code, index) IS the order by (|llr|, index)
+    //      unless two different |llr| share a code, which shows up as an adjacent pair with equal codes and different
+    //      values; then, and for values outside the code's range (NaN, inf, >= 32, tiny), the exact order is found by
+    //      counting (compact, ~4x slower, a few % of the calls).  One compare-exchange is a SHFL and a min/max.
+    uint32_t key[8];
+    bool bad = false;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int i = 32 * r + lane;
-        unsigned long long k = 0ull;
+        uint32_t k = 0u;
         if (i < 174) {
-            const float a = fabsf(llr[i]);
-            const uint32_t u = (a != a) ? 0u : (__float_as_uint(a) + 1u);
-            k = ((unsigned long long)u << 8) | (unsigned long long)(255 - i);
+            const uint32_t u = __float_as_uint(llr[i]) & 0x7FFFFFFFu;
+            const uint32_t e = u >> 23;
+            uint32_t code = 0u;
+            if (u != 0u) {
+                if (e < 101u || e > 131u) bad = true;
+                code = ((e - 100u) << 19) | ((u >> 4) & 0x7FFFFu);
+            }
+            k = (code << 8) | (uint32_t)(255 - i);
         }
         key[r] = k;
     }
+    bad = __any_sync(FULL, bad);
+    if (!bad) {
 #pragma unroll
-    for (int k = 2; k <= 256; k <<= 1) {
+        for (int k = 2; k <= 256; k <<= 1) {
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 32) {                                   // partner slot lives in the same lane
-                const int jr = j >> 5;
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j >= 32) {                                   // partner slot lives in the same lane
+                    const int jr = j >> 5;
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    if ((r & jr) == 0) {
-                        const int e = 32 * r;                // lane bits do not matter for k >= 64
-                        const bool desc = (e & k) == 0;
-                        const unsigned long long x = key[r], y = key[r | jr];
-                        const bool sw = desc ? (x < y) : (x > y);
-                        key[r] = sw ? y : x;
-                        key[r | jr] = sw ? x : y;
+                    for (int r = 0; r < 8; ++r) {
+                        if ((r & jr) == 0) {
+                            const bool desc = ((32 * r) & k) == 0;   // lane bits do not matter for k >= 64
+                            const uint32_t x = key[r], y = key[r | jr];
+                            key[r] = desc ? max(x, y) : min(x, y);
+                            key[r | jr] = desc ? min(x, y) : max(x, y);
+                        }
                     }
-                }
-            } else {                                         // partner slot is in lane ^ j, same register
-                const bool lower = (lane & j) == 0;
+                } else {                                         // partner slot is in lane ^ j, same register
+                    const bool lower = (lane & j) == 0;
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int e = 32 * r + lane;
-                    const bool desc = (e & k) == 0;
-                    const unsigned long long x = key[r];
-                    const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, j);
-                    const bool take_max = (lower == desc);
-                    key[r] = (take_max == (x > y)) ? x : y;
+                    for (int r = 0; r < 8; ++r) {
+                        const bool desc = ((32 * r + lane) & k) == 0;
+                        const uint32_t x = key[r];
+                        const uint32_t y = __shfl_xor_sync(FULL, x, j);
+                        key[r] = (lower == desc) ? max(x, y) : min(x, y);
+                    }
                 }
             }
         }
+        // adjacent sorted slots with equal codes must hold equal values
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            uint32_t nb = __shfl_sync(FULL, key[r], (lane + 1) & 31);
+            const uint32_t nx = __shfl_sync(FULL, key[r + 1], 0);
+            if (lane == 31) nb = nx;
+            if (nb != 0u && ((key[r] ^ nb) >> 8) == 0u) {
+                const uint32_t ua = __float_as_uint(llr[255 - (key[r] & 0xFFu)]) & 0x7FFFFFFFu;
+                const uint32_t ub = __float_as_uint(llr[255 - (nb & 0xFFu)]) & 0x7FFFFFFFu;
+                if (ua != ub) bad = true;
+            }
+        }
+        bad = __any_sync(FULL, bad);
     }
     // ---- 2. publish the order with the hard decisions; rows whose systematic column comes late (position >= 96)
     uint32_t L0 = 0, L1 = 0, L2 = 0;
+    if (!bad) {
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        const int sp = lane + 32 * r;
-        if (sp < 174) {
-            const int c = 255 - (int)(key[r] & 0xFFull);
-            s.order[sp] = (uint16_t)(c | ((llr[c] > 0.0f) ? 0x100 : 0));
-            if (r >= 3 && c < 91) {
-                const uint32_t b = 1u << (c & 31);
-                if (c < 32) L0 |= b; else if (c < 64) L1 |= b; else L2 |= b;
+        for (int r = 0; r < 6; ++r) {
+            const int sp = lane + 32 * r;
+            if (sp < 174) {
+                const int c = 255 - (int)(key[r] & 0xFFu);
+                s.order[sp] = (uint16_t)(c | ((llr[c] > 0.0f) ? 0x100 : 0));
+                if (r >= 3 && c < 91) {
+                    const uint32_t b = 1u << (c & 31);
+                    if (c < 32) L0 |= b; else if (c < 64) L1 |= b; else L2 |= b;
+                }
+            }
+        }
+    } else {
+        // exact order by counting: position of column i = number of columns that precede it
+        // (larger |llr|, or equal |llr| and smaller index; NaN after every number)
+        for (int i = lane; i < 174; i += 32) {
+            const float a = fabsf(llr[i]);
+            const uint32_t ui = (a != a) ? 0u : (__float_as_uint(a) + 1u);
+            int rank = 0;
+            for (int q = 0; q < 174; ++q) {
+                const float aq = fabsf(llr[q]);
+                const uint32_t uq = (aq != aq) ? 0u : (__float_as_uint(aq) + 1u);
+                rank += (uq > ui || (uq == ui && q < i)) ? 1 : 0;
+            }
+            s.order[rank] = (uint16_t)(i | ((llr[i] > 0.0f) ? 0x100 : 0));
+            if (rank >= 96 && i < 91) {
+                const uint32_t b = 1u << (i & 31);
+                if (i < 32) L0 |= b; else if (i < 64) L1 |= b; else L2 |= b;
             }
         }
     }
@@ -239,22 +284,26 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
         syn = __reduce_xor_sync(FULL, syn);
         if (lane == 0) s.syn[0] = (uint16_t)syn;
     }
-    for (int vi = 1; vi < nvec; ++vi) {
-        const int prow = s.piv_row[91 - vi], pcol = s.piv_col[91 - vi];
-        const uint32_t pbit = 1u << (prow & 31);
-        uint32_t syn = (lane == 0) ? (uint32_t)g.syn[pcol < 91 ? pcol : 95] : 0u;       // syn[95] = 0: parity pivots add no unit bit
-        if (prow < 32) {
+    // flip vectors, one per lane: publish the stored columns word-major and let lane i walk the 83 slots for the bit of
+    // its pivot row (a per-vector warp reduction costs 30 x ~40 instructions; this loop ~6 x 83)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) if (c0[k] & pbit) syn ^= slot_syn[k];
-        } else if (prow < 64) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) if (c1[k] & pbit) syn ^= slot_syn[k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) if (c2[k] & pbit) syn ^= slot_syn[k];
-        }
-        syn = __reduce_xor_sync(FULL, syn);
-        if (lane == 0) s.syn[vi] = (uint16_t)syn;
+    for (int k = 0; k < 3; ++k) {
+        const int j = 32 * k + lane;
+        s.colw[j] = c0[k]; s.colw[OSD_W_PITCH + j] = c1[k]; s.colw[2 * OSD_W_PITCH + j] = c2[k];
+        s.ssyn[j] = (uint16_t)slot_syn[k];
+    }
+    __syncwarp();
+    for (int i0 = 0; i0 < S; i0 += 32) {
+        const int i = i0 + lane;
+        const bool act = i < S;
+        const int prow = act ? s.piv_row[90 - i] : 0, pcol = act ? s.piv_col[90 - i] : 255;
+        const uint32_t* cw = s.colw + (prow >> 5) * OSD_W_PITCH;
+        const int sh = prow & 31;
+        uint32_t syn = (uint32_t)g.syn[pcol < 91 ? pcol : 95];           // syn[95] = 0: parity pivots add no unit bit
+#pragma unroll 4
+        for (int q = 0; q < 83; ++q)
+            if ((cw[q] >> sh) & 1u) syn ^= (uint32_t)s.ssyn[q];
+        if (act) s.syn[1 + i] = (uint16_t)syn;
     }
     __syncwarp();
     // 91-bit word of vector vi (-1: none), XOR-accumulated into w0..w2; every lane gets the result

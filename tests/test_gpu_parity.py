@@ -131,6 +131,29 @@ def test_osd_edge_cases_ties_nan_zero(eng):
         assert bits91_to_int(ob[i]) == cands[want - 1 if want else 0]
 
 
+def test_osd_sort_code_collisions_and_out_of_range_magnitudes(eng):
+    """The OSD sorts 24-bit codes of |llr| and must fall back to the exact order when two different magnitudes share a
+    code (they differ only in the low 4 mantissa bits) or a magnitude is outside the code's range (>= 32, < 2^-26, inf)."""
+    rng = np.random.default_rng(21)
+    base, _ = synth.make_llr_codewords(6, 16, 1.5)
+    x = base.copy()
+    one_ulp = lambda v, k: (np.float32(v).view(np.uint32) + np.uint32(k)).view(np.float32)
+    for i in range(0, 4):                                         # distinct values sharing a code, in both index orders
+        a = rng.integers(0, 174, 12)
+        v = np.float32(abs(x[i, a[0]]))
+        for j, q in enumerate(a):
+            x[i, q] = np.float32(one_ulp(v, (j * 5) % 16)) * (1 if x[i, q] > 0 else -1)
+    x[4, 7] = 40.0; x[5, 9] = -1e-9; x[6, 11] = 3e-39; x[7, 13] = np.inf; x[8, 15] = -64.5; x[8, 16] = 64.5
+    x[9, :] *= np.float32(1e-3)                                    # all small but in range
+    x[10, :] *= np.float32(3.0)
+    found, ob = eng.osd(x)
+    for i in range(len(x)):
+        cands = o.osd_candidates(x[i])
+        want = next((k + 1 for k, b in enumerate(cands) if o.crc_ok91(b) and o.valid77(b >> 14)), 0)
+        assert found[i] == want, i
+        assert bits91_to_int(ob[i]) == cands[want - 1 if want else 0], i
+
+
 def test_ldpc_zero_llr_nan_path_like_reference(eng):
     """An llr of exactly 0 gives tanh = 0 and 0/0 = NaN in the reference (decoders.py:144-147); reproduced."""
     llr, _ = synth.make_llr_codewords(8, 4, 3.0)
