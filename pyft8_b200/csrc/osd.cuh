@@ -275,7 +275,6 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
     uint32_t slot_syn[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) slot_syn[k] = (ownrow[k] < 91) ? (uint32_t)g.syn[ownrow[k]] : 0u;
-    const int nvec = 1 + S;
     {
         uint32_t syn = (((hs0 >> lane) & 1u) ? ls.s0 : 0u) ^ (((hs1 >> lane) & 1u) ? ls.s1 : 0u) ^ (((hs2 >> lane) & 1u) ? ls.s2 : 0u);
 #pragma unroll

@@ -57,6 +57,9 @@ if __name__ == "__main__":
                 print("DIFF %s: record count %d vs %d" % (lib, len(a), len(r)))
                 continue
             bad = np.nonzero((a.view(np.uint8).reshape(len(a), -1) != r.view(np.uint8).reshape(len(r), -1)).any(1))[0]
+            if len(bad) == 0:
+                print("DIFF %s: records bit-identical" % lib)
+                continue
             fields = {f: int((a[f][bad] != r[f][bad]).reshape(len(bad), -1).any(1).sum()) for f in a.dtype.names}
             print("DIFF %s: %d records differ; per field %s" % (lib, len(bad), {k: v for k, v in fields.items() if v}))
             for i in bad[:6]:
