@@ -449,9 +449,9 @@ static CandState cand_state(ft8_handle* h) {
 static int launch_spectrogram(ft8_handle* h, const void* d_audio, int dtype, int B, float* d_grid, int row_lo = 1,
                               int row_hi = 375, int out_rows = GRID_ROWS, int out_row0 = 0, int fill_row0 = 1,
                               const void* d_prev_tail = nullptr, int out_wrap = 0) {
+    const bool ring = d_prev_tail != nullptr || out_wrap != 0;
     dim3 grid((row_hi - row_lo + SP_ROWS) / SP_ROWS, B);
     const int smem = SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2);
-    const bool ring = d_prev_tail != nullptr || out_wrap != 0;
 #define SP_LAUNCH(T, RING)                                                                                                          \
     k_spectrogram<T, RING><<<grid, SP_ROWS * SP_NT, smem, h->stream>>>((const T*)d_audio, d_grid, h->d_hann, h->d_TS, h->d_W3840, row_lo, \
                                                                        row_hi, out_rows, out_row0, fill_row0, (const T*)d_prev_tail, out_wrap)

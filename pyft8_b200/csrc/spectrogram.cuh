@@ -10,6 +10,12 @@
 // the first pass reads the windowed audio straight from global memory (int16 -> fp32 fused), the
 // epilogue untangles only the 976 bins that are kept and writes dB.  Rows of one CTA are adjacent,
 // so their 7/8-overlapping windows hit L1/L2: HBM sees the audio once and the grid once.
+//
+// Round-2 experiments that REDUCED the shared-memory / L1 wavefronts per row and still lost (profiles/r02_experiments.md):
+// two adjacent rows per 128-thread group sharing the window and twiddle loads with the untangle fused into the last pass
+// (-22 % wavefronts, 96 registers, 5 CTAs/SM: 12.5 ms vs 7.7), and the fused untangle alone (-10 % wavefronts, z[16] live
+// across two barriers: 9.7 ms).  The kernel is not on a single roof (data pipe 68 %, issue 60 %, FMA 45 % in ncu r02i): it
+// needs its 32 resident warps of short, independent phases more than it needs fewer wavefronts.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
