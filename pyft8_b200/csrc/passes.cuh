@@ -88,10 +88,7 @@ __device__ __forceinline__ void set_result(const CandState& cs, int slot, const 
 
 // ipass 0.  grid: [B][grid_rows][976].  payload_db (optional): [N][58][8].
 // prev[] of the decoder in registers needs ~90 registers: 5 CTAs/SM instead of 8 (measured: 5.80 ms with prev in shared
-// memory at 8 CTAs, 5.02 with the one-reciprocal update, 4.33 with prev in registers at 5 CTAs)
-#ifndef PASS0_PREG
-#define PASS0_PREG true
-#endif
+// memory at 8 CTAs, 5.02 with the cheaper quotients, 4.33 with prev in registers at 5 CTAs)
 #ifndef PASS0_MINB
 #define PASS0_MINB 5
 #endif
@@ -128,16 +125,34 @@ k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows
         ++n_cand;
         const int f0 = cs.f0[slot], h0 = cs.h0[slot];
         const float* g = grid + (size_t)cyc * grid_rows * GRID_COLS;
+        // Payload gather (receiver.py:356-363): 58 symbol rows x 8 tones (the upper bin of each tone).  Lane = 8 * sub + tone
+        // reads row 4 i + sub: the eight tones of a row share one or two 128-byte lines, so a load instruction touches 4-8
+        // lines (one row per lane touched 29: 464 lines per candidate, 2.1x the algorithmic DRAM traffic and most of this
+        // kernel's L1 wavefronts).  The values are handed to the symbol-per-lane layout of the LLR step through shared memory
+        // (the decoder's delta array, idle until the first LDPC iteration).
         float p[2][8];
-        if (lane < 29) {
+        {
+            float* stage = ws.dlt;
+            const int sub = lane >> 3, t = lane & 7;
+            __syncwarp();                         // the previous slot's last LDPC iteration has read dlt
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int sym = lane + (q ? 43 : 7);                  // PAYLOAD_SYMB_IDXS = 7..35, 43..71
-                const int row = cycle_h0 + h0 + 4 + 4 * sym;
+            for (int i = 0; i < 15; ++i) {
+                const int sidx = 4 * i + sub;                             // payload symbol 0..57
+                if (sidx < 58) {
+                    const int sym = sidx < 29 ? sidx + 7 : sidx + 14;      // PAYLOAD_SYMB_IDXS = 7..35, 43..71
+                    const float v = grid_at(g, grid_rows, cycle_h0 + h0 + 4 + 4 * sym, f0 + 1 + 2 * t);
+                    stage[sidx * 8 + t] = v;
+                    if (payload_db) payload_db[((size_t)slot * 58 + sidx) * 8 + t] = v;
+                }
+            }
+            __syncwarp();
+            if (lane < 29) {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    p[q][t] = grid_at(g, grid_rows, row, f0 + 1 + 2 * t);
-                    if (payload_db) payload_db[((size_t)slot * 58 + lane + 29 * q) * 8 + t] = p[q][t];
+                for (int q = 0; q < 2; ++q) {
+                    const float4 a = *reinterpret_cast<const float4*>(stage + (lane + 29 * q) * 8);
+                    const float4 b = *reinterpret_cast<const float4*>(stage + (lane + 29 * q) * 8 + 4);
+                    p[q][0] = a.x; p[q][1] = a.y; p[q][2] = a.z; p[q][3] = a.w;
+                    p[q][4] = b.x; p[q][5] = b.y; p[q][6] = b.z; p[q][7] = b.w;
                 }
             }
         }
@@ -163,7 +178,7 @@ k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows
                 break;
             }
             int nits, iters = 0;
-            const int st = ldpc_warp<PASS0_PREG>(ws, sm.tab, lane, ls, 35, 5, nits, bits, iters);
+            const int st = ldpc_warp(ws, sm.tab, lane, ls, 35, 5, nits, bits, iters);
             ++n_ldpc; n_iter += iters;
             if (st == 1) {
                 if (lane == 0) set_result(cs, slot, bits, 0, ap, 1 /*LDPC5*/, nits);
@@ -232,7 +247,7 @@ k_pass234(CandState cs, const int32_t* __restrict__ list, const int32_t* __restr
             const int ap = p4 ? a - 2 : a;
             apply_ap(ws.llr, llr0, ap, lane);
             int nits, iters = 0;
-            const int st = ldpc_warp<true>(ws, sm.tab, lane, ls, p4 ? 90 : 35, p4 ? 20 : 5, nits, bits, iters);
+            const int st = ldpc_warp(ws, sm.tab, lane, ls, p4 ? 90 : 35, p4 ? 20 : 5, nits, bits, iters);
             ++n_ldpc; n_iter += iters;
             if (st == 1) { if (lane == 0) set_result(cs, slot, bits, p4 ? 4 : 3, ap, p4 ? 2 : 1, nits); done = true; }
             else if (p4 && st >= 2) {                         // FAIL or STALL: reference keeps the llr (receiver.py:128-129)
@@ -351,7 +366,7 @@ k_ldpc_batch(float* __restrict__ llr, int N, int max_ncheck0, int max_iters, int
         __syncwarp();
         uint32_t bits[3];
         int nits, iters = 0;
-        const int st = ldpc_warp<true>(ws, sm.tab, lane, ls, max_ncheck0, max_iters, nits, bits, iters);
+        const int st = ldpc_warp(ws, sm.tab, lane, ls, max_ncheck0, max_iters, nits, bits, iters);
         __syncwarp();
         for (int i = lane; i < 174; i += 32) llr[(size_t)n * 174 + i] = ws.llr[i];
         if (lane == 0) {
