@@ -93,7 +93,7 @@ __device__ __forceinline__ void set_result(const CandState& cs, int slot, const 
 #define PASS0_MINB 5
 #endif
 #ifndef PASS234_MINB
-#define PASS234_MINB 6
+#define PASS234_MINB 5
 #endif
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, PASS0_MINB)
 k_pass0(CandState cs, int n_slots, const float* __restrict__ grid, int grid_rows, int cycle_h0, float sd_min,

@@ -23,7 +23,7 @@ h = rows[1]
 si, ie, ss = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
 sass = [(r[si].strip(), int(r[ie]), int(r[ss]) if r[ss].isdigit() else 0) for r in rows[2:] if len(r) > ie and r[ie].isdigit()]
 # line info from the cubin
-so = os.path.join(ROOT, "pyft8_b200", "libft8_b200.so")
+so = os.environ.get("NCU_SO") or os.path.join(ROOT, "pyft8_b200", "libft8_b200.so")
 tmp = "/tmp/_cubin"
 os.makedirs(tmp, exist_ok=True)
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
