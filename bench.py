@@ -435,9 +435,14 @@ def run_gpu(args, dist, rank, local, world):
     audio = torch.empty((B, 180000), dtype=torch.int16, device=f"cuda:{local}")
     workload.device_cycles(eng, params, audio.data_ptr())
     torch.cuda.synchronize()
-    host = torch.empty((B, 180000), dtype=torch.int16, pin_memory=True)
-    host.copy_(audio)
-    host_np = host.numpy()
+    # the input staging buffer: page-locked memory from the library's allocator (ft8_host_alloc).  FT8_BENCH_HOSTMEM=wc asks
+    # for write-combined memory instead (measured: no difference, 1 GPU 64.6 vs 65.1 k cycles/s, 8 GPUs 357.0 vs 357.6 k --
+    # at 8 GPUs the copies of all ranks together run at the platform's 129 GB/s host-to-device ceiling either way)
+    from pyft8_b200.engine import PinnedArray
+    hostmem = os.environ.get("FT8_BENCH_HOSTMEM", "pinned")
+    host_pin = PinnedArray((B, 180000), np.int16, write_combined=(hostmem == "wc"))
+    host_np = host_pin.array
+    torch.from_numpy(host_np).copy_(audio)
     stream = torch.cuda.ExternalStream(L.load().ft8_stream(eng._h), device=f"cuda:{local}")
     rec = np.zeros(B * eng.max_cands, L.RECORD_DTYPE)
     nrec = np.zeros(B, np.int32)
@@ -526,8 +531,12 @@ def run_gpu(args, dist, rank, local, world):
         e2e = total_cycles * args.steps / (ms_e2e / 1e3)
         e2e_out = {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 360000), "d2h_bytes_per_step": int(n_e2e_decoded * 64 + 4 * B + 96),
                    "ms_per_step": ms_e2e / args.steps,
+                   # all ranks' input copies together: at 8 GPUs this reaches the box's host-to-device ceiling (129 GB/s measured),
+                   # which then bounds e2e (357 k cycles/s) below the kernels (540 k)
+                   "h2d_gb_per_s_all_ranks": round(world * B * 360000 * args.steps / (ms_e2e / 1e3) / 1e9, 2),
                    "gather": {"records_on_rank0_per_step": gathered[0], "bytes_on_rank0_per_step": gathered[1], "segments_pinned": shm_pinned,
                               "how": "sharding.ShmRecordGather: per-rank shared-memory segments + one gloo barrier per step, inside the timed region"} if dist else None,
+                   "host_memory": "write-combined page-locked (ft8_host_alloc)" if hostmem == "wc" else "page-locked (ft8_host_alloc)",
                    "api": "Engine.decode_cycles(pinned host int16, next_audio=...) -> ft8_decode_cycles_stream: one handle, next batch copied under the kernels"}
         # host text formatting of one step's records (outside every timed region): vectorised unpack + de-dup
         from pyft8_b200.receiver import format_records
@@ -572,7 +581,8 @@ def run_gpu(args, dist, rank, local, world):
     configs = None
     if world == 1 and not args.no_configs and not args.device_only:
         eng.close()
-        del audio, host
+        del audio, host_np
+        host_pin.close()
         torch.cuda.empty_cache()
         configs = {"cfg3_fec": config_cfg3_fec(local, args.fec_codewords, args.fec_check),
                    "cfg4_120sig": config_cycles(local, "cfg4_120sig", args.cfg4_cycles, 2, args.seed + 4)}

@@ -20,6 +20,7 @@
 #ifndef FT8_B200_H
 #define FT8_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -199,6 +200,15 @@ int ft8_live_reset(ft8_handle* h);
  * (plain ft8_decode_cycles included, or a streaming call on a different buffer) waits for the pending copy to finish and
  * drops it, so a stale device copy is never decoded and the host buffer is never read after that call returns. */
 int ft8_prefetch_audio(ft8_handle* h, const void* audio_host, int audio_dtype, int B);
+
+/* Page-locked host memory for the streaming entry points (the audio batches a caller refills, the record buffer):
+ * flags bit 0 (FT8_HOST_WRITE_COMBINED) asks for write-combined memory -- meant for INPUT staging buffers the CPU only
+ * writes and the GPU only reads; CPU reads of such memory are very slow.  Memory is portable across devices.  Replaces
+ * nothing in the reference (its audio arrives through PyAudio callbacks, receiver.py:295-306); it exists so that a C or
+ * ctypes caller does not need the CUDA runtime to get DMA-able buffers. */
+#define FT8_HOST_WRITE_COMBINED 1
+int  ft8_host_alloc(size_t bytes, int flags, void** out);
+int  ft8_host_free(void* p);
 
 /* Streaming form of ft8_decode_cycles for host audio: decodes `audio` (consuming its prefetched copy when there is one) and
  * at the same time starts the copy of `next_audio_host` (same dtype and B; NULL = none), i.e. one call per batch with a

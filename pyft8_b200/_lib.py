@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("PYFT8_B200_LIB") or os.path.join(_HERE, "libft8_b200.
 
 OK, E_BADARG, E_CUDA, E_CAPACITY, E_NODEVICE = 0, -1, -2, -3, -4
 MEM_HOST, MEM_DEVICE = 0, 1
+HOST_WRITE_COMBINED = 1
 AUDIO_I16, AUDIO_F32 = 0, 1
 GRID_ROWS, GRID_ROWS_LIVE, GRID_COLS, SPEC_BINS = 376, 750, 976, 96001
 LDPC_REJECT, LDPC_OK, LDPC_FAIL, LDPC_STALL = 0, 1, 2, 3
@@ -71,6 +72,8 @@ SIGNATURES = {
     "ft8_osd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]),
     "ft8_crc14": (C.c_int, [_P, _P, C.c_int, _P, C.c_int]),
     "ft8_prefetch_audio": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "ft8_host_alloc": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(_P)]),
+    "ft8_host_free": (C.c_int, [_P]),
     "ft8_decode_cycles": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int]),
     "ft8_decode_cycles_live": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int]),
     "ft8_live_reset": (C.c_int, [_P]),

@@ -418,6 +418,19 @@ extern "C" void ft8_destroy(ft8_handle* h) {
 
 extern "C" const char* ft8_last_error(ft8_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 extern "C" void* ft8_stream(ft8_handle* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int ft8_host_alloc(size_t bytes, int flags, void** out) {
+    if (!out || bytes == 0) return FT8_E_BADARG;
+    *out = nullptr;
+    unsigned f = cudaHostAllocPortable;
+    if (flags & FT8_HOST_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+    if (cudaHostAlloc(out, bytes, f) != cudaSuccess) { cudaGetLastError(); *out = nullptr; return FT8_E_CUDA; }
+    return FT8_OK;
+}
+extern "C" int ft8_host_free(void* p) {
+    if (!p) return FT8_OK;
+    if (cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return FT8_E_CUDA; }
+    return FT8_OK;
+}
 extern "C" int ft8_synchronize(ft8_handle* h) {
     if (!h) return FT8_E_BADARG;
     CK(cudaSetDevice(h->device));

@@ -59,6 +59,36 @@ class _SerialisedLib:
         return getattr(self._tls, "err", "")
 
 
+class PinnedArray:
+    """Page-locked host array from the library's allocator (ft8_host_alloc): `.array` is a numpy view, freed on close() /
+    garbage collection.  write_combined=True is for input staging buffers the CPU only writes (CPU reads are very slow)."""
+
+    def __init__(self, shape, dtype, write_combined=False):
+        lib = L.load()
+        self._lib = lib
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        rc = lib.ft8_host_alloc(nbytes, L.HOST_WRITE_COMBINED if write_combined else 0, C.byref(p))
+        if rc != L.OK or not p.value:
+            raise RuntimeError("ft8_host_alloc(%d bytes) failed: rc %d" % (nbytes, rc))
+        self._p = p
+        self.array = np.frombuffer((C.c_uint8 * nbytes).from_address(p.value), dtype=dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_p", None) is not None:
+            self.array = None
+            self._lib.ft8_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+
 class Engine:
     def __init__(self, device=0, max_cycles=1, max_cands=200, sync_score_min=85.0, llr_sd_min=5.0,
                  osd_singleflips=30, osd_doubleflips=2, fine_mode=0,
