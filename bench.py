@@ -506,11 +506,15 @@ def run_gpu(args, dist, rank, local, world):
         shm = ShmRecordGather(dist, B * eng.max_cands, L.RECORD_DTYPE, tag=os.environ.get("MASTER_PORT", "0")) if dist else None
         shm_pinned = shm.pin() if shm else None
 
+        step_wall = []
+
         def e2e_steps(k):
             r_i = None
+            del step_wall[:]
             # step 0 is not prefetched: its copy runs in chunks with the front-end kernels starting as chunks land (and is
             # inside the timed region like every other step's); from step 1 on the copy hides under the previous step
             for i in range(k):
+                t_i = time.perf_counter()
                 # N > 1: the records are copied back straight into this rank's shared-memory slot (pinned with cudaHostRegister)
                 out = shm.slot_array() if shm else rec_np
                 r_i, _ = eng.decode_cycles(host_np, next_audio=host_np if i + 1 < k else None, rec=out, n=n_np)
@@ -519,6 +523,7 @@ def run_gpu(args, dist, rank, local, world):
                     parts = shm.collect()                 # barrier; rank 0 now sees every rank's records of this step
                     if rank == 0:
                         gathered[0], gathered[1] = sum(len(p) for p in parts), sum(p.nbytes for p in parts)
+                step_wall.append(1e3 * (time.perf_counter() - t_i))
             return r_i
 
         e2e_steps(min(args.warmup, 2))
@@ -531,6 +536,10 @@ def run_gpu(args, dist, rank, local, world):
         e2e = total_cycles * args.steps / (ms_e2e / 1e3)
         e2e_out = {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 360000), "d2h_bytes_per_step": int(n_e2e_decoded * 64 + 4 * B + 96),
                    "ms_per_step": ms_e2e / args.steps,
+                   # the timed region starts cold: step 0's input copy cannot hide under a previous step (it runs in chunks
+                   # with the front-end kernels); the steps after it are the steady state of a stream (rank 0's wall clock)
+                   "first_step_ms": round(step_wall[0], 3) if step_wall else None,
+                   "steady_state_ms_per_step": round(float(np.median(step_wall[1:])), 3) if len(step_wall) > 1 else None,
                    # all ranks' input copies together: at 8 GPUs this reaches the box's host-to-device ceiling (129 GB/s measured),
                    # which then bounds e2e (357 k cycles/s) below the kernels (540 k)
                    "h2d_gb_per_s_all_ranks": round(world * B * 360000 * args.steps / (ms_e2e / 1e3) / 1e9, 2),

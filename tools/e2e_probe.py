@@ -21,3 +21,11 @@ for i in range(4):
     print("streamed call: wall %.2f ms, device %.2f ms, stages %s" % (1e3 * (t1 - t0), eng.last_kernel_ms(0), [round(eng.last_kernel_ms(k), 2) for k in range(1, 9)]))
 t0 = time.perf_counter(); eng.decode_cycles(host_np, rec=rec_np, n=n_np); t1 = time.perf_counter()
 print("last (prefetched, no next): wall %.2f ms, device %.2f ms" % (1e3 * (t1 - t0), eng.last_kernel_ms(0)))
+# raw host->device rate of the same pinned buffer (is the streamed call copy-bound?)
+dst = torch.empty_like(audio)
+for _ in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); dst.copy_(host, non_blocking=True); torch.cuda.synchronize(); t1 = time.perf_counter()
+    print("H2D 1.47 GB: %.2f ms = %.1f GB/s" % (1e3 * (t1 - t0), host.numel() * 2 / (t1 - t0) / 1e9))
+small = torch.empty((17_000_000,), dtype=torch.uint8).pin_memory(); dsm = torch.empty_like(small, device="cuda:0")
+torch.cuda.synchronize(); t0 = time.perf_counter(); small.copy_(dsm, non_blocking=True); torch.cuda.synchronize(); t1 = time.perf_counter()
+print("D2H 17 MB: %.2f ms" % (1e3 * (t1 - t0)))
