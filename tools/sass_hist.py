@@ -40,7 +40,7 @@ def main():
             kern = re.sub(r"\(.*", "", name).replace("ft8::", "").replace("void ", "")
             hist[kern] = collections.Counter()
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*(?:\.[A-Z0-9_.]+)?)", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*(?:\.[A-Z0-9_.]+)?)", line)
         if m and kern:
             hist[kern][m.group(1)] += 1
     print(f"# SASS opcode histogram per kernel — `cuobjdump -sass {os.path.relpath(so, ROOT)}` (static instruction counts, sm_100a)\n")
