@@ -45,7 +45,7 @@ WANT = {
     "fadd_per_cycle": "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed",
     "fmul_per_cycle": "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed",
     "thread_inst": "thread_inst_executed",
-    "warp_inst": "sm__inst_executed.sum",
+    "warp_inst": "smsp__inst_executed.sum",
     "grid": "Grid Size",
     "block": "Block Size",
 }
