@@ -202,6 +202,57 @@ def decode_two_cycles(audio_a, audio_b, t0=30.0 * 1000000, workdir=None):
         os.chdir(cwd)
 
 
+def decode_cycle_progressive(audio_i16, extra_hops=120, t0=30.0 * 1000000, workdir=None):
+    """One cycle through the unmodified reference the way its scheduler THREAD sees it (receiver.py:376-412), made
+    deterministic: after every 480-sample hop the body of manage_cycle's loop runs exactly once -- reset the searched flag
+    at a cycle start, decode every candidate whose payload rows are complete (sorted by llr_sd), search once the hop
+    counter passes search_start_hop (hop 260 = 10.4 s).  `extra_hops` hops of silence follow the cycle so that the late
+    candidates get their turn.  Returns dict(messages, emit_hop) -- emit_hop[i] = hop after which message i came out."""
+    rx, dec, tx, db, tu = load_reference()
+    clock = tu.time_utils._clock
+    audio_i16 = np.asarray(audio_i16, dtype=np.int16)
+    db.call_hashes.clear()
+    cwd = os.getcwd()
+    if workdir:
+        os.chdir(workdir)
+    try:
+        clock.now = t0
+        msgs, emit_hop = [], []
+        r = rx.Receiver("", msgs.append)
+        ai = r.audio_in
+        dup = set()
+        prev = 0
+        searched = False
+        silence = np.zeros(480, np.int16).tobytes()
+        n_cands = 0
+        for k in range(375 + extra_hops):
+            clock.now = t0 + (k + 1) * 0.04 + 1e-6
+            ai._callback(audio_i16[480 * k:480 * (k + 1)].tobytes() if k < 375 else silence, 480, None, None)
+            pos = ai.search_grid_ptr % ai.search_hops_per_cycle
+            if pos < prev:
+                searched = False
+            prev = pos
+            todo = [c for c in r.candidates if (not c.decode_result) and
+                    (not (c.search_grid_bounds[0] <= ai.search_grid_ptr <= c.search_grid_bounds[1]))]
+            if todo:
+                todo.sort(key=lambda c: c.llr_sd, reverse=True)
+                max_ipass = 10 + min(c.ipass for c in todo)
+                for c in todo:
+                    c.decode(max_ipass)
+                    if c.decode_result is not None and c.decode_result != "stop":
+                        n0 = len(msgs)
+                        c.check_and_package(dup)
+                        emit_hop += [k + 1] * (len(msgs) - n0)
+            if not searched and pos > r.search_start_hop:
+                cs = tu.time_utils.cyclestart_string(clock.now)
+                r.candidates = r.search(cs, tu.time_utils.odd_even(), range(ai.search_f0_idx_range[0], ai.search_f0_idx_range[1]))
+                n_cands = len(r.candidates)
+                searched = True
+        return dict(messages=msgs, emit_hop=emit_hop, n_cands=n_cands, pending=sum(1 for c in r.candidates if not c.decode_result))
+    finally:
+        os.chdir(cwd)
+
+
 def read_wav_i16(path):
     import wave
     w = wave.open(path, "rb")

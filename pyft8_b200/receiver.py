@@ -437,23 +437,31 @@ class Receiver:
                 c.check_and_package(duplicate_filter)
         return len(todo)
 
-    def manage_cycle(self):
-        duplicate_filter = set()
-        prev = 0
-        searched = False
+    def new_cycle_state(self):
+        return {"duplicate_filter": set(), "prev": 0, "searched": False}
+
+    def tick(self, st):
+        """One iteration of the reference's scheduler loop (receiver.py:379-412, without its sleep): reset the searched flag
+        at a cycle start, decode every candidate whose payload rows are complete, search once the hop counter has passed
+        search_start_hop.  manage_cycle() calls it every 100 ms; tests call it once per hop to make the thread's behaviour
+        deterministic (oracle/ref_harness.decode_cycle_progressive drives the unmodified reference the same way)."""
         ai = self.audio_in
+        pos = ai.search_grid_ptr % ai.search_hops_per_cycle
+        if pos < st["prev"]:
+            st["searched"] = False
+        st["prev"] = pos
+        self.step(st["duplicate_filter"])
+        if not st["searched"] and pos > self.search_start_hop:
+            cs = self._tu.cyclestart_string(self._tu.time())
+            self.candidates = self.search(cs, self._tu.odd_even(),
+                                          range(ai.search_f0_idx_range[0], ai.search_f0_idx_range[1]))
+            st["searched"] = True
+
+    def manage_cycle(self):
+        st = self.new_cycle_state()
         while True:
             self._tu.sleep(0.1)
-            pos = ai.search_grid_ptr % ai.search_hops_per_cycle
-            if pos < prev:
-                searched = False
-            prev = pos
-            self.step(duplicate_filter)
-            if not searched and pos > self.search_start_hop:
-                cs = self._tu.cyclestart_string(self._tu.time())
-                self.candidates = self.search(cs, self._tu.odd_even(),
-                                              range(ai.search_f0_idx_range[0], ai.search_f0_idx_range[1]))
-                searched = True
+            self.tick(st)
 
     # ------------------------------------------------------------------ batched entry (ours)
     def decode_cycles(self, audio, odd_even=0, cyclestart_strings=None, emit=True):

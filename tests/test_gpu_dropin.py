@@ -62,7 +62,7 @@ def test_receiver_live_surface_matches_reference(name, golden_cycles):
     assert np.all(ai.search_grid[376:] == 1.0) and np.all(ai.search_grid[0] == 1.0)
     now[0] = 30.0 * 1000000 + 15.0
     cands = rx.search("CS", 0, range(32, 960))
-    assert [c.origin["f0_idx"] for c in cands] == list(g["cand_f0"]) or len(set(c.origin["f0_idx"] for c in cands) ^ set(g["cand_f0"].tolist())) <= 4
+    assert [c.origin["f0_idx"] for c in cands] == list(g["cand_f0"])            # content and rank, no tolerance
     rx.candidates = cands
     dup = set()
     for _ in range(9):
@@ -84,6 +84,89 @@ def test_receiver_live_surface_matches_reference(name, golden_cycles):
     assert mb.text[kept].tolist() == list(g["msg_text"])
     assert mb.notes(kept) == list(g["msg_notes"])
     assert mb.lines() == [m["all_txt_format"].replace(m["cyclestart_string"], "CS", 1) if m["cyclestart_string"] else "CS" + m["all_txt_format"] for m in out]
+
+
+@pytest.mark.parametrize("name", ["test_08", "syn20"])
+def test_progressive_scheduler_equals_reference_hop_by_hop(name, golden_cycles):
+    """The reference's time-gated scheduler (receiver.py:376-412) made deterministic: the loop body runs once after every
+    hop (Receiver.tick), so the search happens at hop 260 (10.4 s) and every candidate is decoded as soon as its payload
+    rows are on the grid -- before the trailing Costas block and the rest of the cycle are in the audio ring.  Golden:
+    the unmodified reference driven the same way (oracle/make_golden_progressive.py): same messages, same order, same
+    notes, each emitted after the same hop."""
+    from pyft8_b200 import messages
+    from pyft8_b200.receiver import Receiver
+    audio, _ = golden_cycles[name]
+    g = load_golden("progressive.npz")
+    messages.call_hashes.clear()
+    now = [30.0 * 1000000]
+    msgs, hops = [], []
+    hop = [0]
+    rx = Receiver("", lambda m: (msgs.append(m), hops.append(hop[0])), clock=lambda: now[0])
+    ai = rx.audio_in
+    st = rx.new_cycle_state()
+    silence = np.zeros(480, np.int16).tobytes()
+    for k in range(375 + 120):
+        hop[0] = k + 1
+        now[0] = 30.0 * 1000000 + (k + 1) * 0.04 + 1e-6
+        ai._callback(audio[480 * k:480 * (k + 1)].tobytes() if k < 375 else silence, 480, None, None)
+        rx.tick(st)
+    assert all(c.decode_result for c in rx.candidates) and len(rx.candidates) > 0
+    assert [" ".join(m["msg_tuple"]) for m in msgs] == g[f"{name}_text"].tolist()
+    assert [m["decode_notes"] for m in msgs] == g[f"{name}_notes"].tolist()
+    assert [int(m["their_snr"]) for m in msgs] == g[f"{name}_snr"].tolist()
+    assert hops == g[f"{name}_hop"].tolist()
+    assert min(hops) > 260 and min(hops) < 375                     # the first decodes arrive before the cycle is complete
+
+
+def test_manage_cycle_thread_runs_the_same_scheduler(golden_cycles):
+    """Same scheduler on its own thread with the audio callback on another (the live configuration; one handle, calls
+    serialised by the engine lock).  Which hop a candidate is decoded after depends on thread timing -- in the reference
+    too -- so this only checks what does not: nothing is emitted twice, nothing outside the end-of-cycle decode set
+    appears, the strong majority of it does, and the first messages arrive before the cycle ends."""
+    import threading
+    import time
+    from pyft8_b200 import messages
+    from pyft8_b200.receiver import Receiver
+    audio, g = golden_cycles["test_08"]
+    messages.call_hashes.clear()
+    now = [30.0 * 1000000]
+    lock = threading.Lock()
+    msgs, at_hop = [], []
+    hop = [0]
+
+    def on_message(m):
+        with lock:
+            msgs.append(m)
+            at_hop.append(hop[0])
+
+    rx = Receiver("", on_message, clock=lambda: now[0], start_thread=True)
+    ai = rx.audio_in
+    silence = np.zeros(480, np.int16).tobytes()
+    want = g["msg_text"].tolist()
+    deadline = time.time() + 120
+
+    def idle():
+        c = rx.candidates
+        return len(c) > 0 and all(x.decode_result for x in c)
+
+    for k in range(375 + 200):                                   # the cycle, then at most 8 s of the next one
+        hop[0] = k + 1
+        now[0] = 30.0 * 1000000 + (k + 1) * 0.04 + 1e-6
+        ai._callback(audio[480 * k:480 * (k + 1)].tobytes() if k < 375 else silence, 480, None, None)
+        time.sleep(0.004)                                        # the scheduler thread polls a fake clock every <= 10 ms
+        if k >= 375 and idle():
+            break
+        assert time.time() < deadline
+    while not idle() and time.time() < deadline:
+        time.sleep(0.05)
+    assert idle()
+    with lock:
+        got = [" ".join(m["msg_tuple"]) for m in msgs]
+        first = min(at_hop) if at_hop else None
+    assert len(got) == len(set(got))                              # de-duplicated like receiver.py:53-55
+    assert set(got) <= set(want)
+    assert len(got) >= len(want) - 6
+    assert first is not None and 260 < first <= 375, first
 
 
 @pytest.mark.gpu
