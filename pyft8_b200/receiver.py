@@ -444,7 +444,7 @@ class Receiver:
         """One iteration of the reference's scheduler loop (receiver.py:379-412, without its sleep): reset the searched flag
         at a cycle start, decode every candidate whose payload rows are complete, search once the hop counter has passed
         search_start_hop.  manage_cycle() calls it every 100 ms; tests call it once per hop to make the thread's behaviour
-        deterministic (oracle/ref_harness.decode_cycle_progressive drives the unmodified reference the same way)."""
+        deterministic (the golden run of tests/golden/progressive.npz drives the unmodified reference the same way)."""
         ai = self.audio_in
         pos = ai.search_grid_ptr % ai.search_hops_per_cycle
         if pos < st["prev"]:
