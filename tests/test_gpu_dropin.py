@@ -169,6 +169,28 @@ def test_manage_cycle_thread_runs_the_same_scheduler(golden_cycles):
     assert first is not None and 260 < first <= 375, first
 
 
+def test_library_pinned_buffers_carry_a_streamed_decode():
+    """ft8_host_alloc / ft8_host_free through engine.PinnedArray: audio in plain and write-combined page-locked memory and
+    a page-locked record buffer give the same records as ordinary numpy arrays."""
+    from pyft8_b200 import _lib as L
+    from pyft8_b200.engine import PinnedArray
+    a = np.stack([synth.make_cycle(s, n_signals=6, snr_db=(-10, 4))[0] for s in (11, 12)])
+    eng = Engine(max_cycles=2)
+    want, n_want = eng.decode_cycles(a)
+    want = want.copy()
+    for wc in (False, True):
+        pa = PinnedArray(a.shape, np.int16, write_combined=wc)
+        pr = PinnedArray((2 * eng.max_cands,), L.RECORD_DTYPE)
+        pa.array[:] = a
+        got, n = eng.decode_cycles(pa.array, next_audio=pa.array, rec=pr.array)
+        assert np.array_equal(n, n_want) and got.tobytes() == want.tobytes()
+        got2, _ = eng.decode_cycles(pa.array, rec=pr.array)              # consumes the prefetched copy
+        assert got2.tobytes() == want.tobytes()
+        pa.close(); pr.close()
+        assert pa.array is None
+    eng.close()
+
+
 @pytest.mark.gpu
 def test_streaming_decode_equals_plain_decode():
     """ft8_prefetch_audio / ft8_decode_cycles_stream: the look-ahead copy changes when bytes move, not what is decoded."""
