@@ -29,6 +29,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "codec.cuh"
 
 namespace ft8 {
@@ -41,9 +42,10 @@ __constant__ OsdTables c_osd;
 constexpr int OSD_MAX_FLIPS = 91;
 
 struct OsdWarpScratch {
-    uint16_t order[176];             // sorted position -> original column | hard decision << 8
+    uint32_t order[176];             // sorted position -> entry | hard decision << 8 (32-bit: no sub-word extraction in the visit loop)
     uint8_t piv_row[96];             // pivot k -> row
-    uint8_t piv_col[96];             // pivot k -> original column
+    uint8_t piv_col[96];             // pivot k -> original column (255: a parity column)
+    uint8_t pcol[96];                // parity rank (position among the parity columns in reliability order) -> column
     uint16_t syn[OSD_MAX_FLIPS + 1]; // CRC syndrome of [0] the order-0 word, [1+i] the vector that flip i adds
     uint16_t ssyn[96];               // CRC syndrome of the systematic column whose image slot j holds (0: not a basis slot)
     uint32_t colw[3 * 97];           // the stored columns word-major [3][OSD_W_PITCH] (odd pitch: the three words of a slot
@@ -86,6 +88,22 @@ __device__ __forceinline__ uint32_t sel3(int w, uint32_t a0, uint32_t a1, uint32
           "+r"(ownrow[0]), "+r"(ownrow[1]), "+r"(ownrow[2])                                                               \
         : "r"(pb), "r"(x0), "r"(x1), "r"(j), "r"(lane), "r"(p), "r"(T0), "r"(T1), "r"(T2), "r"(x2))
 
+
+// The same step when the pivot's slot is known at compile time (a parity column of rank j lives in slot j/32, and parity
+// columns are visited in rank order, so the visit loop runs through the three slots one after the other): only the own
+// slot A needs the "not my own lane" test, and no slot has to be selected at run time.
+#define OSD_ELIM_S(A, B, D, TA, TB, TD)                                                                                   \
+    asm("{\n .reg .pred q0, q1, q2, n0;\n .reg .b32 t0, t1, t2;\n"                                                        \
+        " setp.eq.s32 n0, %14, %15;\n"                                                                                     \
+        " and.b32 t0, %17, %10;\n and.b32 t1, %18, %10;\n and.b32 t2, %19, %10;\n"                                        \
+        " setp.ne.and.b32 q0, t0, 0, !n0;\n setp.ne.b32 q1, t1, 0;\n setp.ne.b32 q2, t2, 0;\n"                            \
+        " @q0 xor.b32 %0, %0, %11;\n @q0 xor.b32 %1, %1, %12;\n @q0 xor.b32 %2, %2, %13;\n"                               \
+        " @q1 xor.b32 %3, %3, %11;\n @q1 xor.b32 %4, %4, %12;\n @q1 xor.b32 %5, %5, %13;\n"                               \
+        " @q2 xor.b32 %6, %6, %11;\n @q2 xor.b32 %7, %7, %12;\n @q2 xor.b32 %8, %8, %13;\n"                               \
+        " @n0 mov.b32 %9, %16;\n}"                                                                                         \
+        : "+r"(c0[A]), "+r"(c1[A]), "+r"(c2[A]), "+r"(c0[B]), "+r"(c1[B]), "+r"(c2[B]), "+r"(c0[D]), "+r"(c1[D]), "+r"(c2[D]), \
+          "+r"(ownrow[A])                                                                                                 \
+        : "r"(pb), "r"(x0), "r"(x1), "r"(x2), "r"(jl), "r"(lane), "r"(p), "r"(TA), "r"(TB), "r"(TD))
 
 // Returns trial index + 1 of the first accepted trial word (0 = none); bits = that word.
 // llr: 174 floats in shared or global memory.
@@ -158,15 +176,23 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
         }
         bad = __any_sync(FULL, bad);
     }
-    // ---- 2. publish the order with the hard decisions; rows whose systematic column comes late (position >= 96)
+    // ---- 2. publish the order with the hard decisions: entry = column for a systematic column, 128 + parity rank for a parity
+    //      column (its rank among the parity columns in reliability order = the slot it will live in); rows whose
+    //      systematic column comes late (position >= 96)
     uint32_t L0 = 0, L1 = 0, L2 = 0;
     if (!bad) {
+        int pbase = 0;
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
             const int sp = lane + 32 * r;
+            const int c = 255 - (int)(key[r] & 0xFFu);
+            const bool isp = sp < 174 && c >= 91;
+            const uint32_t bal = __ballot_sync(FULL, isp);
+            const int prank = pbase + __popc(bal & ((1u << lane) - 1u));
+            pbase += __popc(bal);
             if (sp < 174) {
-                const int c = 255 - (int)(key[r] & 0xFFu);
-                s.order[sp] = (uint16_t)(c | ((llr[c] > 0.0f) ? 0x100 : 0));
+                if (isp) s.pcol[prank] = (uint8_t)c;
+                s.order[sp] = (uint32_t)((isp ? 128 + prank : c) | ((llr[c] > 0.0f) ? 0x100 : 0));
                 if (r >= 3 && c < 91) {
                     const uint32_t b = 1u << (c & 31);
                     if (c < 32) L0 |= b; else if (c < 64) L1 |= b; else L2 |= b;
@@ -175,17 +201,20 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
         }
     } else {
         // exact order by counting: position of column i = number of columns that precede it
-        // (larger |llr|, or equal |llr| and smaller index; NaN after every number)
+        // (larger |llr|, or equal |llr| and smaller index; NaN after every number); parity rank = the parity columns among them
         for (int i = lane; i < 174; i += 32) {
             const float a = fabsf(llr[i]);
             const uint32_t ui = (a != a) ? 0u : (__float_as_uint(a) + 1u);
-            int rank = 0;
+            int rank = 0, prank = 0;
             for (int q = 0; q < 174; ++q) {
                 const float aq = fabsf(llr[q]);
                 const uint32_t uq = (aq != aq) ? 0u : (__float_as_uint(aq) + 1u);
-                rank += (uq > ui || (uq == ui && q < i)) ? 1 : 0;
+                const int before = (uq > ui || (uq == ui && q < i)) ? 1 : 0;
+                rank += before;
+                prank += (q >= 91) ? before : 0;
             }
-            s.order[rank] = (uint16_t)(i | ((llr[i] > 0.0f) ? 0x100 : 0));
+            if (i >= 91) s.pcol[prank] = (uint8_t)i;
+            s.order[rank] = (uint32_t)((i >= 91 ? 128 + prank : i) | ((llr[i] > 0.0f) ? 0x100 : 0));
             if (rank >= 96 && i < 91) {
                 const uint32_t b = 1u << (i & 31);
                 if (i < 32) L0 |= b; else if (i < 64) L1 |= b; else L2 |= b;
@@ -193,14 +222,15 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
         }
     }
     L0 = __reduce_or_sync(FULL, L0); L1 = __reduce_or_sync(FULL, L1); L2 = __reduce_or_sync(FULL, L2);
-    // ---- 3. the 83 parity columns (slot r of lane l: parity column 32 r + l), eliminated in place
+    // ---- 3. the 83 parity columns (slot r of lane l: the parity column of rank 32 r + l), eliminated in place
+    __syncwarp();
     uint32_t c0[3], c1[3], c2[3];
     uint32_t ownrow[3];               // row (= systematic column) whose image the slot holds, 255: not a basis slot
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const int j = 32 * r + lane;
         ownrow[r] = 255;
-        if (j < 83) { c0[r] = g.col[91 + j]; c1[r] = g.col[OSD_COL_PITCH + 91 + j]; c2[r] = g.col[2 * OSD_COL_PITCH + 91 + j]; }
+        if (j < 83) { const int col = s.pcol[j]; c0[r] = g.col[col]; c1[r] = g.col[OSD_COL_PITCH + col]; c2[r] = g.col[2 * OSD_COL_PITCH + col]; }
         else c0[r] = c1[r] = c2[r] = 0u;
     }
     uint32_t own0 = 0, own1 = 0, own2 = 0;        // slot holding the image of row lane / 32 + lane / 64 + lane
@@ -208,15 +238,54 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
     uint32_t u0 = 0, u1 = 0, u2 = 0;              // u[row] = hard decision of that row's pivot column
     uint32_t hs0 = 0, hs1 = 0, hs2 = 0;           // hard decisions of the basis' systematic columns, by column
     int npiv = 0;
-    __syncwarp();
+    // One visit of a stored column (slot j, fetched as v0..v2): dependent -> false; else pick the pivot row, do the
+    // bookkeeping and eliminate.  JR = 0..2: the slot index is static (parity column in rank order); JR = 3: dynamic (the
+    // stored image of a systematic column).  csys = the systematic column being visited, or 255.
+    auto visit = [&](auto JRc, uint32_t v0, uint32_t v1, uint32_t v2, int j, int jl, int csys, bool hb) -> bool {
+        constexpr int JR = decltype(JRc)::value;
+        const uint32_t f0 = v0 & ~used0, f1 = v1 & ~used1, f2 = v2 & ~used2;
+        if ((f0 | f1 | f2) == 0) return false;    // dependent column
+        uint32_t g0 = f0 & L0, g1 = f1 & L1, g2 = f2 & L2;
+        if ((g0 | g1 | g2) == 0) { g0 = f0; g1 = f1; g2 = f2; }
+        const int pw = g0 ? 0 : (g1 ? 1 : 2);
+        const uint32_t gw = g0 ? g0 : (g1 ? g1 : g2);
+        const uint32_t pb = gw & (0u - gw);
+        const int pl = 31 - __clz(pb);
+        const int p = 32 * pw + pl;
+        if (lane == 0) { s.piv_row[npiv] = (uint8_t)p; s.piv_col[npiv] = (uint8_t)csys; }
+        if (JR == 3 && hb) {
+            const uint32_t b = 1u << (csys & 31);
+            if (csys < 32) hs0 |= b; else if (csys < 64) hs1 |= b; else hs2 |= b;
+        }
+        // pw is warp-uniform: three copies of the update, each testing a fixed word
+        uint32_t x0 = v0, x1 = v1, x2 = v2;       // the pivot column with the pivot row cleared
+        constexpr int A = JR < 3 ? JR : 0, B = (A + 1) % 3, D = (A + 2) % 3;
+        if (pw == 0) {
+            used0 |= pb; if (hb) u0 |= pb;
+            if (lane == pl) own0 = (uint32_t)j;
+            x0 &= ~pb;
+            if (JR < 3) { OSD_ELIM_S(A, B, D, c0[A], c0[B], c0[D]); } else { OSD_ELIM(c0[0], c0[1], c0[2]); }
+        } else if (pw == 1) {
+            used1 |= pb; if (hb) u1 |= pb;
+            if (lane == pl) own1 = (uint32_t)j;
+            x1 &= ~pb;
+            if (JR < 3) { OSD_ELIM_S(A, B, D, c1[A], c1[B], c1[D]); } else { OSD_ELIM(c1[0], c1[1], c1[2]); }
+        } else {
+            used2 |= pb; if (hb) u2 |= pb;
+            if (lane == pl) own2 = (uint32_t)j;
+            x2 &= ~pb;
+            if (JR < 3) { OSD_ELIM_S(A, B, D, c2[A], c2[B], c2[D]); } else { OSD_ELIM(c2[0], c2[1], c2[2]); }
+        }
+        return true;
+    };
     uint32_t e_next = s.order[0];
     for (int sp = 0; sp < 174; ++sp) {
         const uint32_t e = e_next;
         e_next = s.order[sp + 1];                 // order[] is padded; the entry after the last one is never used
         const int c = (int)(e & 0xFFu);
         const bool hb = (e >> 8) != 0;
-        int j;
-        if (c < 91) {
+        bool piv;
+        if (c < 128) {                            // systematic column c
             const int w = c >> 5;
             const uint32_t b = 1u << (c & 31);
             if ((sel3(w, used0, used1, used2) & b) == 0) {        // untouched unit vector on a free row: nothing to eliminate
@@ -224,50 +293,26 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
                 else if (w == 1) { used1 |= b; if (hb) { u1 |= b; hs1 |= b; } }
                 else { used2 |= b; if (hb) { u2 |= b; hs2 |= b; } }
                 if (lane == 0) { s.piv_row[npiv] = (uint8_t)c; s.piv_col[npiv] = (uint8_t)c; }
-                if (++npiv == 91) break;
-                continue;
+                piv = true;
+            } else {                                               // its image lives in a basis slot
+                const int j = (int)__shfl_sync(FULL, sel3(w, own0, own1, own2), c & 31);
+                const int jl = j & 31, jr = j >> 5;
+                const uint32_t v0 = __shfl_sync(FULL, sel3(jr, c0[0], c0[1], c0[2]), jl);
+                const uint32_t v1 = __shfl_sync(FULL, sel3(jr, c1[0], c1[1], c1[2]), jl);
+                const uint32_t v2 = __shfl_sync(FULL, sel3(jr, c2[0], c2[1], c2[2]), jl);
+                piv = visit(std::integral_constant<int, 3>{}, v0, v1, v2, j, jl, c, hb);
             }
-            j = (int)__shfl_sync(FULL, sel3(w, own0, own1, own2), c & 31);       // its image lives in a basis slot
-        } else {
-            j = c - 91;
+        } else {                                  // parity column of rank j: slot j / 32 of lane j % 32
+            const int j = c - 128, jl = j & 31;
+            if (j < 32) {
+                piv = visit(std::integral_constant<int, 0>{}, __shfl_sync(FULL, c0[0], jl), __shfl_sync(FULL, c1[0], jl), __shfl_sync(FULL, c2[0], jl), j, jl, 255, hb);
+            } else if (j < 64) {
+                piv = visit(std::integral_constant<int, 1>{}, __shfl_sync(FULL, c0[1], jl), __shfl_sync(FULL, c1[1], jl), __shfl_sync(FULL, c2[1], jl), j, jl, 255, hb);
+            } else {
+                piv = visit(std::integral_constant<int, 2>{}, __shfl_sync(FULL, c0[2], jl), __shfl_sync(FULL, c1[2], jl), __shfl_sync(FULL, c2[2], jl), j, jl, 255, hb);
+            }
         }
-        const int jl = j & 31, jr = j >> 5;
-        const uint32_t v0 = __shfl_sync(FULL, sel3(jr, c0[0], c0[1], c0[2]), jl);
-        const uint32_t v1 = __shfl_sync(FULL, sel3(jr, c1[0], c1[1], c1[2]), jl);
-        const uint32_t v2 = __shfl_sync(FULL, sel3(jr, c2[0], c2[1], c2[2]), jl);
-        const uint32_t f0 = v0 & ~used0, f1 = v1 & ~used1, f2 = v2 & ~used2;
-        if ((f0 | f1 | f2) == 0) continue;        // dependent column
-        uint32_t g0 = f0 & L0, g1 = f1 & L1, g2 = f2 & L2;
-        if ((g0 | g1 | g2) == 0) { g0 = f0; g1 = f1; g2 = f2; }
-        const int pw = g0 ? 0 : (g1 ? 1 : 2);
-        const uint32_t gw = sel3(pw, g0, g1, g2);
-        const uint32_t pb = gw & (0u - gw);
-        const int pl = 31 - __clz(pb);
-        const int p = 32 * pw + pl;
-        if (lane == 0) { s.piv_row[npiv] = (uint8_t)p; s.piv_col[npiv] = (uint8_t)c; }
-        if (c < 91 && hb) {
-            const uint32_t b = 1u << (c & 31);
-            if (c < 32) hs0 |= b; else if (c < 64) hs1 |= b; else hs2 |= b;
-        }
-        // pw is warp-uniform: three copies of the update, each testing a fixed word
-        uint32_t x0 = v0, x1 = v1, x2 = v2;       // the pivot column with the pivot row cleared
-        if (pw == 0) {
-            used0 |= pb; if (hb) u0 |= pb;
-            if (lane == pl) own0 = (uint32_t)j;
-            x0 &= ~pb;
-            OSD_ELIM(c0[0], c0[1], c0[2]);
-        } else if (pw == 1) {
-            used1 |= pb; if (hb) u1 |= pb;
-            if (lane == pl) own1 = (uint32_t)j;
-            x1 &= ~pb;
-            OSD_ELIM(c1[0], c1[1], c1[2]);
-        } else {
-            used2 |= pb; if (hb) u2 |= pb;
-            if (lane == pl) own2 = (uint32_t)j;
-            x2 &= ~pb;
-            OSD_ELIM(c2[0], c2[1], c2[2]);
-        }
-        if (++npiv == 91) break;
+        if (piv && ++npiv == 91) break;
     }
     __syncwarp();
     // ---- 4. CRC syndromes of the 1+S vectors (vector 0 = order-0 word, vector 1+i = what flip i adds).  Only the 14-bit
@@ -330,8 +375,7 @@ __device__ __forceinline__ int osd_warp(OsdWarpScratch& s, const OsdCtaTables& g
     // ---- 5. enumerate trials in the reference's order; first with payload != 0, CRC ok, valid payload
     //      trial 0: base; 1..S: single flips i = 0..S-1; then pairs (i, j), j < D, j < i, i-major.
     const int nsingle = S;
-    int npair = 0;
-    for (int i = 0; i < S; ++i) npair += min(i, D);
+    const int npair = (S <= D) ? S * (S - 1) / 2 : D * (D - 1) / 2 + (S - D) * D;      // sum over i < S of min(i, D)
     const int ntrial = 1 + nsingle + npair;
     const int tri = D * (D - 1) / 2;               // pairs of the rows i < D (row i has i of them); every later row has D
     const uint32_t bs = s.syn[0];
