@@ -90,7 +90,7 @@ __device__ __forceinline__ void set_result(const CandState& cs, int slot, const 
 // prev[] of the decoder in registers needs ~90 registers: 5 CTAs/SM instead of 8 (measured: 5.80 ms with prev in shared
 // memory at 8 CTAs, 5.02 with the cheaper quotients, 4.33 with prev in registers at 5 CTAs)
 #ifndef PASS0_MINB
-#define PASS0_MINB 5
+#define PASS0_MINB 4
 #endif
 #ifndef PASS234_MINB
 #define PASS234_MINB 5
@@ -276,7 +276,10 @@ struct OsdSmem {
 };
 
 // ipass 5-6: item = 10 * list index + attempt.  attempts 0..4: AP pattern on the fine llr; 5..9: saved llr.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
+#ifndef OSD_MINB
+#define OSD_MINB 8
+#endif
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, OSD_MINB)
 k_osd_items(CandState cs, const int32_t* __restrict__ list, const int32_t* __restrict__ count, int S, int D,
             int32_t* __restrict__ next_item, DevStats* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char pass_smem_raw[];
