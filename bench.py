@@ -540,8 +540,8 @@ def run_gpu(args, dist, rank, local, world):
                    # with the front-end kernels); the steps after it are the steady state of a stream (rank 0's wall clock)
                    "first_step_ms": round(step_wall[0], 3) if step_wall else None,
                    "steady_state_ms_per_step": round(float(np.median(step_wall[1:])), 3) if len(step_wall) > 1 else None,
-                   # all ranks' input copies together: at 8 GPUs this reaches the box's host-to-device ceiling (129 GB/s measured),
-                   # which then bounds e2e (357 k cycles/s) below the kernels (540 k)
+                   # all ranks' input copies together: at 8 GPUs this reaches the box's host-to-device ceiling (134 GB/s measured),
+                   # which then bounds e2e (372 k cycles/s) below the kernels (563 k)
                    "h2d_gb_per_s_all_ranks": round(world * B * 360000 * args.steps / (ms_e2e / 1e3) / 1e9, 2),
                    "gather": {"records_on_rank0_per_step": gathered[0], "bytes_on_rank0_per_step": gathered[1], "segments_pinned": shm_pinned,
                               "how": "sharding.ShmRecordGather: per-rank shared-memory segments + one gloo barrier per step, inside the timed region"} if dist else None,
