@@ -113,7 +113,8 @@ typedef struct ft8_record {
 typedef struct ft8_stats {
     int64_t cycles, candidates, stopped_sd, fine_evals, fine_pass, ldpc_calls, ldpc_iters, osd_calls,
             decoded, emitted, kernel_launches;
-    int64_t reserved[5];
+    int64_t fine_rechecked;      /* candidates whose frequency scan was a near-tie and was decided by the literal kernel */
+    int64_t reserved[4];
 } ft8_stats;
 
 /* Fills cfg with the reference defaults (max_cycles = 1). */

@@ -38,7 +38,7 @@ class Record(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("cycles", "candidates", "stopped_sd", "fine_evals", "fine_pass",
                                          "ldpc_calls", "ldpc_iters", "osd_calls", "decoded", "emitted",
-                                         "kernel_launches")] + [("reserved", C.c_int64 * 5)]
+                                         "kernel_launches", "fine_rechecked")] + [("reserved", C.c_int64 * 4)]
 
 
 # numpy structured dtype with the same layout as ft8_record

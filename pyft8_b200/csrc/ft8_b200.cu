@@ -47,6 +47,7 @@ struct ft8_handle {
     // tensor-core frequency scan (fine_tc.cuh): B operand (E | M, tf32 hi/lo), half-sample phase table, per-item intermediates
     float* d_bmat = nullptr; float2* d_w6400 = nullptr;
     float2* d_zwin = nullptr; TScanOut* d_tso = nullptr; int32_t* d_ff = nullptr; size_t fine_tmp_items = 0;
+    int32_t* d_amb = nullptr;         // [fine_tmp_items + 1]: near-tie candidates of the frequency scan ([0] = count, list from [1])
     // batch scratch
     size_t cap_cycles = 0, cap_slots = 0;
     void* d_audio = nullptr; size_t audio_bytes = 0;
@@ -379,7 +380,7 @@ extern "C" int ft8_create(int device, const ft8_cfg* cfg_in, ft8_handle** out) {
     CKC(cudaFuncSetAttribute(k_fscan_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES));
     if (cfg.fine_mode == 0) {
         h->fine_tmp_items = N;
-        CKC(dmalloc(&h->d_zwin, N * FS_WIN)); CKC(dmalloc(&h->d_tso, N)); CKC(dmalloc(&h->d_ff, N));
+        CKC(dmalloc(&h->d_zwin, N * FS_WIN)); CKC(dmalloc(&h->d_tso, N)); CKC(dmalloc(&h->d_ff, N)); CKC(dmalloc(&h->d_amb, N + 1));
     }
     {
         const int sp_smem = SP_ROWS * SP_BUFS * SP_BUF_LEN * (int)sizeof(float2);
@@ -400,7 +401,7 @@ extern "C" void ft8_destroy(ft8_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_TS, h->d_TF, h->d_TC, h->d_T256, h->d_W96000T, h->d_hann, h->d_W1920, h->d_W3840, h->d_W3200, h->d_W375, h->d_W256, h->d_W96000, h->d_W192000, h->d_W32,
-                    h->d_pulse, h->d_ring, h->d_tail, h->d_bmat, h->d_w6400, h->d_zwin, h->d_tso, h->d_ff, h->d_audio, h->d_grid, h->d_Y, h->d_spec, h->d_best_score, h->d_best_h0, h->d_f0, h->d_h0, h->d_score,
+                    h->d_pulse, h->d_ring, h->d_tail, h->d_bmat, h->d_w6400, h->d_zwin, h->d_tso, h->d_ff, h->d_amb, h->d_audio, h->d_grid, h->d_Y, h->d_spec, h->d_best_score, h->d_best_h0, h->d_f0, h->d_h0, h->d_score,
                     h->d_ncand, h->d_cycle_of, h->d_status, h->d_llr_grid, h->d_grid_sd, h->d_grid_snr, h->d_llr_fine, h->d_fine,
                     h->d_saved, h->d_saved_n, h->d_saved_ap, h->d_bits, h->d_ripass, h->d_rap, h->d_rmethod, h->d_rnits,
                     h->d_osd_found, h->d_osd_bits, h->d_list_fine, h->d_list_osd, h->d_counts, h->d_stats, h->d_rec, h->d_rec_n, h->d_rec_base, h->arena};
@@ -524,8 +525,9 @@ static int launch_fine(ft8_handle* h, const float2* spec, int spec_stride, const
     if (need > h->fine_tmp_items) {
         CK(cudaStreamSynchronize(h->stream));
         if (h->d_zwin) CK(cudaFree(h->d_zwin)); if (h->d_tso) CK(cudaFree(h->d_tso)); if (h->d_ff) CK(cudaFree(h->d_ff));
-        h->d_zwin = nullptr; h->d_tso = nullptr; h->d_ff = nullptr; h->fine_tmp_items = 0;
-        CK(dmalloc(&h->d_zwin, need * FS_WIN)); CK(dmalloc(&h->d_tso, need)); CK(dmalloc(&h->d_ff, need));
+        if (h->d_amb) CK(cudaFree(h->d_amb));
+        h->d_zwin = nullptr; h->d_tso = nullptr; h->d_ff = nullptr; h->d_amb = nullptr; h->fine_tmp_items = 0;
+        CK(dmalloc(&h->d_zwin, need * FS_WIN)); CK(dmalloc(&h->d_tso, need)); CK(dmalloc(&h->d_ff, need)); CK(dmalloc(&h->d_amb, need + 1));
         h->fine_tmp_items = need;
     }
     const int nbt = list ? persistent_blocks(h, FT_CTAS) : std::min(persistent_blocks(h, FT_CTAS), n_direct);
@@ -534,16 +536,21 @@ static int launch_fine(ft8_handle* h, const float2* spec, int spec_stride, const
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[12], h->stream));
     const int nb1 = list ? h->n_sm : std::min(h->n_sm, (n_direct + FS_CAND - 1) / FS_CAND);
+    CK(cudaMemsetAsync(h->d_amb, 0, sizeof(int32_t), h->stream));
     k_fscan_mma<<<nb1, FS_NT, FS_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_tso, h->d_zwin,
-                                                         h->d_bmat, h->d_w6400, h->d_ff);
+                                                         h->d_bmat, h->d_w6400, h->d_ff, h->d_amb + 1, h->d_amb);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[13], h->stream));
     k_fine_final<FT_NT, FF_CTAS><<<nb3, FT_NT, FF_SMEM_BYTES, h->stream>>>(spec, spec_stride, list, count, n_direct, cycle_of, f0, h0, h->d_TF, h->d_tso, h->d_ff,
                                                             fo, llr, sig_grid);
     CK(cudaGetLastError());
+    // near-tie candidates of the frequency scan: decided by the literal nine-transform kernel (overwrites their results)
+    k_fine<<<persistent_blocks(h, 2), FINE_NT, FINE_SMEM_BYTES, h->stream>>>(spec, spec_stride, h->d_amb + 1, h->d_amb, 0, cycle_of, f0, h0, h->d_TF, fo, llr, sig_grid);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->d_counts + 3, h->d_amb, sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));      // statistics: counts[3]
     return FT8_OK;
 }
-static int fine_launches(ft8_handle* h) { return h->cfg.fine_mode == 1 ? 1 : 3; }
+static int fine_launches(ft8_handle* h) { return h->cfg.fine_mode == 1 ? 1 : 4; }
 
 // copy helpers honouring the mem flag
 static int to_device(ft8_handle* h, void* d, const void* src, size_t bytes, int mem) {
@@ -1160,6 +1167,7 @@ static int decode_cycles_core(ft8_handle* h, const void* audio, int audio_dtype,
     s.fine_evals = (int64_t)h->h_stats->fine_evals; s.fine_pass = (int64_t)h->h_stats->fine_pass;
     s.ldpc_calls = (int64_t)h->h_stats->ldpc_calls; s.ldpc_iters = (int64_t)h->h_stats->ldpc_iters;
     s.osd_calls = (int64_t)h->h_stats->osd_calls; s.decoded = nrec; s.emitted = emitted; s.kernel_launches = launches;
+    s.fine_rechecked = h->cfg.fine_mode == 0 ? h->h_counts[3] : 0;
     if (overflow) return fail(h, FT8_E_CAPACITY, "ft8_decode_cycles: rec_capacity too small (records truncated)");
     return FT8_OK;
 }
